@@ -1,0 +1,97 @@
+"""Tiling, per-patch normalisation and overlap-blend stitch (oracle; test infrastructure only).
+
+Restates (numpy, like the reference):
+  * ``patch_iter``      -- Patch.py:80-84   (row-major sliding window; right/bottom remainder not covered)
+  * ``build_mask``      -- Patch.py:41-49   (all inputs finite [and target finite, collocation > 0])
+  * window slicing      -- Patch.py:201-203
+  * valid-ratio filter  -- Patch.py:205-209
+  * ``zscore_inplace``  -- Patch.py:51-62 applied to HH, HV over valid pixels (Patch.py:228-229)
+  * incidence/90, elevation/1000 with nan->0 -- Patch.py:231-232
+  * invalid -> 0 and nan/inf -> 0 -- Patch.py:236-239
+
+``stitch`` is NOT in the reference: parity unpinned.  Definition adopted:
+canvas[c,y,x] = sum_p w * pred_p[c, y-r_p, x-c_p] / sum_p w with uniform w = 1, patches accumulated in
+index order; pixels covered by no patch are 0 and flagged 0 in the coverage mask.
+"""
+import numpy as np
+
+
+def tile_origins(H: int, W: int, ps: int, stride: int) -> np.ndarray:
+    """int32[N,2] (row, col) in the reference's iteration order."""
+    rows = range(0, H - ps + 1, stride)
+    cols = range(0, W - ps + 1, stride)
+    return np.array([(r, c) for r in rows for c in cols], dtype=np.int32).reshape(-1, 2)
+
+
+def valid_mask(inputs: np.ndarray, target: np.ndarray = None, colloc: np.ndarray = None) -> np.ndarray:
+    m = np.isfinite(inputs).all(axis=0)
+    if target is not None:
+        m &= np.isfinite(target).all(axis=0)
+    if colloc is not None:
+        m &= colloc > 0
+    return m
+
+
+def _zscore(x: np.ndarray, m: np.ndarray) -> None:
+    if m is None or not m.any():
+        mu, sd = np.nanmean(x), np.nanstd(x)
+    else:
+        mu, sd = float(np.nanmean(x[m])), float(np.nanstd(x[m]))
+    if not np.isfinite(mu):
+        mu = 0.0
+    if not np.isfinite(sd) or sd < 1e-6:
+        sd = 1.0
+    x -= mu
+    x /= sd
+
+
+def extract_patch(inputs: np.ndarray, vmask: np.ndarray, row: int, col: int, ps: int):
+    """One window -> (cond f32[4,ps,ps], mask u8[ps,ps], valid_ratio).  inputs = (HH dB, HV dB, incidence deg,
+    elevation m) as float32 [4,H,W]."""
+    X = inputs[:, row:row + ps, col:col + ps].astype(np.float32).copy()
+    M = vmask[row:row + ps, col:col + ps].copy()
+    vr = float(M.mean()) if M.size else 0.0
+    with np.errstate(all="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _zscore(X[0], M)
+            _zscore(X[1], M)
+    X[2] = np.nan_to_num(X[2], nan=0.0) / 90.0
+    X[3] = np.nan_to_num(X[3], nan=0.0) / 1000.0
+    for ch in range(X.shape[0]):
+        a = X[ch]
+        a[~M] = 0.0
+        X[ch] = np.nan_to_num(a, nan=0.0, posinf=0.0, neginf=0.0).astype(np.float32)
+    return X, M.astype(np.uint8), vr
+
+
+def extract_all(inputs: np.ndarray, vmask: np.ndarray, ps: int, stride: int, valid_ratio_threshold: float = 0.0):
+    """All windows in order; windows whose valid ratio is below the threshold are skipped (Patch.py:205-209)."""
+    H, W = inputs.shape[1:]
+    idx, conds, masks = [], [], []
+    for r, c in tile_origins(H, W, ps, stride):
+        X, M, vr = extract_patch(inputs, vmask, int(r), int(c), ps)
+        if vr < valid_ratio_threshold:
+            continue
+        idx.append((r, c)); conds.append(X); masks.append(M)
+    n = len(idx)
+    return (np.array(idx, dtype=np.int32).reshape(n, 2),
+            np.stack(conds) if n else np.zeros((0, inputs.shape[0], ps, ps), np.float32),
+            np.stack(masks) if n else np.zeros((0, ps, ps), np.uint8))
+
+
+def stitch(preds: np.ndarray, origins: np.ndarray, H: int, W: int):
+    """Uniform-weight overlap blend.  preds f32[N,C,ps,ps], origins i32[N,2] -> (canvas f32[C,H,W], cover u8[H,W]).
+
+    Accumulates in fp32 in patch-index order and divides once, which is the exact arithmetic the CUDA gather
+    kernel performs per output pixel."""
+    N, C, ps, _ = preds.shape
+    acc = np.zeros((C, H, W), np.float32)
+    cnt = np.zeros((H, W), np.float32)
+    for p in range(N):
+        r, c = int(origins[p, 0]), int(origins[p, 1])
+        acc[:, r:r + ps, c:c + ps] += preds[p]
+        cnt[r:r + ps, c:c + ps] += 1.0
+    out = np.where(cnt > 0, acc / np.maximum(cnt, 1.0), 0.0).astype(np.float32)
+    return out, (cnt > 0).astype(np.uint8)
