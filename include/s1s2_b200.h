@@ -1,0 +1,129 @@
+/* libs1s2_b200.so -- C ABI of the B200-native S1->S2 diffusion sampling path.
+ *
+ * The reference (ChenghanXia/S1-to-S2_Super-Resolution_Project-Code) is pure Python/PyTorch and has no FFI; its
+ * "operator interface" for this path is the Python callable `model(torch.cat([x_t, x_cond], 1), t_idx)` plus free
+ * sampler functions taking `model`.  Each entry point below names the reference call site
+ * it replaces; the Python mirror of those call sites (`s1s2_b200.UNetSmallB200`, `s1s2_b200.samplers`) binds these
+ * symbols with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device pointer is caller-owned (e.g. torch tensor .data_ptr()).
+ *   - all image tensors are float32, contiguous NCHW, exactly like the reference's tensors.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Work is stream-ordered and
+ *     asynchronous unless stated; there is no CPU fallback: without a B200-class device every call fails.
+ *   - return value 0 = success, non-zero = error (message via s1s2_last_error / s1s2_global_error);
+ *     no C++ exception crosses the boundary.
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef S1S2_B200_H
+#define S1S2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct s1s2_handle s1s2_handle;
+
+enum {
+    S1S2_OK = 0,
+    S1S2_ERR_INVALID = 1,   /* bad argument / unsupported geometry */
+    S1S2_ERR_CUDA = 2,      /* CUDA runtime / driver error */
+    S1S2_ERR_STATE = 3      /* e.g. weights not loaded */
+};
+
+/* Scheduler-update kinds evaluated in the epilogue of the network's last convolution. */
+enum {
+    S1S2_STEP_NONE = 0,      /* plain model call */
+    S1S2_STEP_EPS_DDIM = 1,  /* x0=(x-c0*e)/c1; x'=c2*x0+c3*e (+c4*z)   Evaluation/DDIM_Multi-step.py:129-133 */
+    S1S2_STEP_V_DDIM = 2,    /* x0=c0*x-c1*v; e=c1*x+c0*v; x' as above  DDIM_Multi-step_v_Prediction.py:59-65,161-174 */
+    S1S2_STEP_EPS_DDPM = 3,  /* x'=c2*(x-c3*e) (+c4*z)                  Evaluation/Limitation_Test.py:213-223 */
+    S1S2_STEP_V_DDPM = 4     /* e=c1*x+c0*v first                        Limitation_Test_v_Prediction.py:214-225 */
+};
+enum {
+    S1S2_STEP_FINAL = 1,     /* result = clamp(x0,0,1) (DDIM kinds) / clamp(x',0,1) (DDPM kinds) */
+    S1S2_STEP_NOISE = 2      /* add c4 * z, z taken from the step_noise argument */
+};
+
+/* One model call + scheduler update.  The host computes the coefficients exactly as the reference would
+ * (float32 torch arithmetic on the float32 alpha_bar table) so the fused update is bit-identical to the
+ * reference's elementwise code given the same network output. */
+typedef struct s1s2_step {
+    int32_t t;          /* timestep fed to the network for this call */
+    int32_t kind;       /* S1S2_STEP_* */
+    int32_t flags;      /* S1S2_STEP_FINAL | S1S2_STEP_NOISE */
+    int32_t noise_index;/* index into step_noise[...] when S1S2_STEP_NOISE is set */
+    float c0, c1, c2, c3, c4;
+} s1s2_step;
+
+/* Replaces `UNetSmall(in_ch, out_ch, base_ch).to(device)` (Evaluation/DDIM_Multi-step.py:19-41; call site
+ * DDIM_Multi-step_v_Prediction.py:263).  Allocates the fp16 NHWC activation arena for `max_batch` patches of
+ * H x W on `device`.  Supported: in_ch=8, out_ch=4, base_ch=96, H and W multiples of 16. */
+int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_ch, int H, int W, int max_batch);
+
+/* Replaces `model.load_state_dict(state, strict=True)` (DDIM_Multi-step_v_Prediction.py:264-271).  `names[i]` are
+ * the reference's 34 state_dict keys, `ptrs[i]` float32 DEVICE pointers in the reference's layouts (Conv2d OIHW,
+ * ConvTranspose2d IOHW), `numel[i]` their element counts.  Strict: every key must be present with the right size.
+ * Weights are repacked to fp16 [cout][tap][cin]; the time plane is folded into two fp16 input planes. */
+int s1s2_load_weights(s1s2_handle* h, int n, const char* const* names, const float* const* ptrs,
+                      const int64_t* numel, void* stream);
+
+/* Replaces `model(torch.cat([x_t, x_cond], dim=1), t_idx)` (Evaluation/DDIM_Multi-step.py:43-53,131).
+ * xt_and_cond: f32[B,8,H,W]; t_idx: int64[B]; out: f32[B,4,H,W] (all device). */
+int s1s2_forward(s1s2_handle* h, const float* xt_and_cond, const int64_t* t_idx, float* out, int B, void* stream);
+
+/* Replaces the whole sampling loop of ddpm_ddim_generate / ddim_multistep_eval[_v] / ddim_sample / sample_ddim_v /
+ * ddpm_sample / sample_ddpm_v (call sites listed in SURVEY.md section 8 a3-a10): n_steps model calls with the
+ * scheduler update fused into the last convolution's epilogue; no host synchronisation inside.
+ *   steps      host array [n_steps]
+ *   cond       f32[B,4,H,W] device
+ *   x_init     f32[B,4,H,W] device; the state starts as x_init * init_scale
+ *   step_noise f32[n_noise,B,4,H,W] device or NULL
+ *   out        f32[B,4,H,W] device: the sampler state, holds the result when the stream drains
+ *   tap_pred   f32[n_steps,B,4,H,W] device or NULL: network output (eps or v) of every call
+ *   tap_x      f32[n_steps,B,4,H,W] device or NULL: state after every update */
+int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond, const float* x_init,
+                float init_scale, const float* step_noise, float* out, float* tap_pred, float* tap_x, int B,
+                void* stream);
+
+/* Same as s1s2_sample with HOST buffers (pinned memory recommended): copies cond / x_init to the device, samples,
+ * copies the result back and synchronises the stream.  This is the end-to-end entry a host-side caller of the
+ * reference scripts would bind (they load .npz patches on the CPU, DDIM_Multi-step.py:104-111). */
+int s1s2_sample_host(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond_host,
+                     const float* x_init_host, float init_scale, float* out_host, int B, void* stream);
+
+/* Tile extraction + per-patch normalisation (Patch.py:80-84,201-209,226-239) for the windows listed in `origins`.
+ *   scene   f32[4,SH,SW] device (HH dB, HV dB, incidence deg, elevation m; may hold NaN/Inf)
+ *   vmask   u8[SH,SW] device or NULL: extra validity (Patch.py:41-49's target / collocation terms); a pixel is
+ *           valid when all four scene channels are finite and vmask (if given) is non-zero
+ *   origins int32[N,2] device (row, col)
+ *   cond    f32[N,4,ps,ps] device out; mask u8[N,ps,ps] device out; valid_ratio f32[N] device out (nullable) */
+int s1s2_tile_extract(int device, const float* scene, const uint8_t* vmask, int SH, int SW, const int32_t* origins,
+                      int N, int ps, float* cond, uint8_t* mask, float* valid_ratio, void* stream);
+
+/* Uniform-weight overlap blend (not in the reference; definition in DESIGN.md): gather formulation, deterministic.
+ *   preds f32[N,C,ps,ps] device; origins int32[N,2] device, sorted in Patch.py iteration order on a regular
+ *   `stride` grid; canvas f32[C,SH,SW] and cover u8[SH,SW] device out. */
+int s1s2_stitch(int device, const float* preds, const int32_t* origins, int N, int C, int ps, int stride, int SH,
+                int SW, float* canvas, uint8_t* cover, void* stream);
+
+/* Per-layer parity tap: converts the named activation of the LAST model call (fp16 NHWC arena view) to float32
+ * NCHW.  Names follow the network's blocks: "inc", "down1", "down2", "down3", "up3", "conv3", "up2", "conv2",
+ * "up1", plus the mid-block tensors "down1.0", "down2.0", "down3.0", "conv3.0", "conv2.0", "conv1.0" and the
+ * packed input record "xin16".  With out_nchw == NULL only the shape (C, H, W) is returned. */
+int s1s2_debug_activation(s1s2_handle* h, const char* name, float* out_nchw, int B, int* C, int* H, int* W,
+                          void* stream);
+
+/* Number of kernels this library launched on behalf of `h` since creation (bench.py's gpu_launches). */
+int64_t s1s2_launch_count(const s1s2_handle* h);
+
+const char* s1s2_last_error(const s1s2_handle* h);
+const char* s1s2_global_error(void);   /* for the handle-less entry points and failed s1s2_create */
+void s1s2_destroy(s1s2_handle* h);
+int s1s2_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S1S2_B200_H */

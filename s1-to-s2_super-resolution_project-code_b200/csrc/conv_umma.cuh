@@ -1,0 +1,361 @@
+// Implicit-GEMM convolution for the UNetSmall denoiser on sm_100a: TMA-fed, tcgen05.mma with the accumulator in
+// TMEM, warp-specialised and persistent (one CTA per SM).
+//
+//   D[pixel, cout] = sum_{tap, cin} X[pixel shifted by tap, cin] * Wt[cout, tap, cin]
+//
+// Reference semantics being reproduced (Evaluation/DDIM_Multi-step.py:19-53): nn.Conv2d(k=3, padding=1) + ReLU,
+// nn.MaxPool2d(2) after the second conv of each encoder block, nn.ConvTranspose2d(k=2, stride=2) (no activation),
+// torch.cat skips (realised by writing producers into halves of one NHWC buffer), and the 1x1 `outc` head, whose
+// epilogue also applies the DDIM/DDPM scheduler update of the samplers (DDIM_Multi-step.py:129-133 etc.).
+//
+// Data layout: activations NHWC fp16; a 128-pixel M tile is a TN x TH x TW block of pixels fetched by ONE 4-D TMA
+// box per (tap, channel chunk) at coordinates shifted by (kx-1, ky-1) -- out-of-image rows/columns are zero-filled
+// by the TMA unit, which is exactly the conv's zero padding.  Weights are [cout][tap][cin] fp16 (K-major), one 2-D
+// TMA box per chunk.  Both operands land in the canonical K-major swizzled layout UMMA reads.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 =
+// epilogue (TMEM lane quadrant = warp_idx % 4).  Two TMEM accumulators so the epilogue of tile i overlaps the MMAs
+// of tile i+1.
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace s1s2 {
+
+enum : int { MODE_STORE = 0, MODE_POOL = 1, MODE_CONVT = 2, MODE_HEAD = 3 };
+
+enum : int { STEP_NONE = 0, STEP_EPS_DDIM = 1, STEP_V_DDIM = 2, STEP_EPS_DDPM = 3, STEP_V_DDPM = 4 };
+enum : int { STEP_FLAG_FINAL = 1, STEP_FLAG_NOISE = 2 };
+
+// One scheduler update; travels by value in the kernel parameters, so a sampling loop is enqueued (or captured in
+// a CUDA graph) without device-side bookkeeping or host round trips.
+//  EPS_DDIM: x0 = (x - c0*e)/c1            ; xn = c2*x0 + c3*e  (+ c4*z)
+//  V_DDIM  : x0 = c0*x - c1*v, e = c1*x + c0*v ; xn = c2*x0 + c3*e  (+ c4*z)
+//  EPS_DDPM: xn = c2*(x - c3*e) (+ c4*z)   ; V_DDPM: e = c1*x + c0*v first
+//  FINAL   : result = clamp(x0, 0, 1) for DDIM kinds, clamp(xn, 0, 1) for DDPM kinds
+struct StepCoef {
+    float c0, c1, c2, c3, c4;
+    float t_next;   // timestep planted into the next call's time planes
+    int kind;
+    int flags;
+};
+
+constexpr int kHeadIn = 96;   // conv1.2 output channels == outc input channels (base_ch)
+constexpr int kHeadOut = 4;
+
+struct HeadParams {
+    float w[kHeadOut * kHeadIn];  // outc.weight [4][96]
+    float b[kHeadOut];
+    float* x_t;                   // f32 NCHW [B,4,H,W], updated in place (nullptr for a plain forward)
+    float* pred_out;              // f32 NCHW eps / v (nullable)
+    const float* noise;           // f32 NCHW per-step z (nullable)
+    __half* xin16;                // next call's input planes, NHWC16 fp16 (nullable)
+    StepCoef step;                // by value: kind == STEP_NONE for a plain forward
+};
+
+struct ConvParams {
+    CUtensorMap tmap_a;
+    CUtensorMap tmap_b;
+    const float* bias;            // [num_n_tiles * BLOCK_N]
+    __half* out;                  // NHWC fp16 destination (channel offset already applied)
+    int out_cpitch;               // elements between consecutive destination pixels
+    int H, W, B;                  // input image size, live batch
+    int tw_log2, th_log2;         // M tile = TN x TH x TW = 128 pixels
+    int tiles_x, tiles_y;
+    int num_m_tiles, num_n_tiles;
+    int taps_w;                   // 3 -> 3x3 pad 1 ; 1 -> 1x1 / transposed-conv GEMM
+    int chunks;                   // K chunks of KBOX channels per tap
+    int cout;                     // real channels per output pixel (CONVT: per tap)
+    HeadParams head;              // MODE_HEAD only
+};
+
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES>
+struct ConvSmem {
+    static constexpr int kABox = 128 * KBOX * 2;
+    static constexpr int kBBox = BLOCK_N * KBOX * 2;
+    static constexpr int kStage = BOXES * (kABox + kBBox);
+    static constexpr int kBias = 1536 * 4;
+    static constexpr int kBytes = 1024 /*align slack*/ + STAGES * kStage + kBias + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE>
+__global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
+    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES>;
+    static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
+    static_assert(KBOX == 16 || KBOX == 32 || KBOX == 64, "KBOX");
+    constexpr int kRowBytes = KBOX * 2;
+    constexpr int kAccStride = 256;            // TMEM columns between the two accumulators
+    constexpr uint32_t kIdesc = umma_idesc_f16(128, BLOCK_N);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    float* sbias = reinterpret_cast<float*>(smem + STAGES * L::kStage);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage + L::kBias);
+    uint64_t* full_bar = bars;                    // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int k_iters = (p.taps_w * p.taps_w * p.chunks) / BOXES;
+    const int pad = p.taps_w >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmap_a);
+        tma_prefetch_desc(&p.tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);       // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    {   // bias for every N tile of this layer, staged once
+        const int nb = p.num_n_tiles * BLOCK_N;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) sbias[i] = p.bias[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.num_n_tiles;
+                const int m_tile = tile / p.num_n_tiles;
+                const int tx = m_tile % p.tiles_x;
+                const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+                const int tn = m_tile / (p.tiles_x * p.tiles_y);
+                const int x0 = tx << p.tw_log2;
+                const int y0 = ty << p.th_log2;
+                const int n0 = tn << (7 - p.tw_log2 - p.th_log2);
+                int box = 0;
+                for (int it = 0; it < k_iters; ++it) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], L::kStage);
+                    uint8_t* a_dst = stage_base + s * L::kStage;
+                    uint8_t* b_dst = a_dst + BOXES * L::kABox;
+#pragma unroll
+                    for (int b = 0; b < BOXES; ++b, ++box) {
+                        const int tap = box / p.chunks;
+                        const int chunk = box - tap * p.chunks;
+                        const int ky = tap / p.taps_w;
+                        const int kx = tap - ky * p.taps_w;
+                        tma_load_4d(a_dst + b * L::kABox, &p.tmap_a, &full_bar[s], chunk * KBOX, x0 + kx - pad,
+                                    y0 + ky - pad, n0);
+                        tma_load_2d(b_dst + b * L::kBBox, &p.tmap_b, &full_bar[s], box * KBOX, n_tile * BLOCK_N);
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            int acc = 0;
+            uint32_t acc_ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kAccStride;
+                for (int it = 0; it < k_iters; ++it) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(stage_base + s * L::kStage);
+                    const uint32_t b_addr = a_addr + BOXES * L::kABox;
+#pragma unroll
+                    for (int b = 0; b < BOXES; ++b) {
+                        const uint64_t adesc = umma_smem_desc<kRowBytes>(a_addr + b * L::kABox);
+                        const uint64_t bdesc = umma_smem_desc<kRowBytes>(b_addr + b * L::kBBox);
+#pragma unroll
+                        for (int k = 0; k < KBOX / 16; ++k) {
+                            // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
+                            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (it | b | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);                 // smem slot reusable once these MMAs retire
+                    if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_ph ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================= epilogue (4 warps, 1 pixel per thread)
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int tw = 1 << p.tw_log2;
+        const int lx = m & (tw - 1);
+        const int ly = (m >> p.tw_log2) & ((1 << p.th_log2) - 1);
+        const int ln = m >> (p.tw_log2 + p.th_log2);
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.num_n_tiles;
+            const int m_tile = tile / p.num_n_tiles;
+            const int tx = m_tile % p.tiles_x;
+            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+            const int tn = m_tile / (p.tiles_x * p.tiles_y);
+            const int x = (tx << p.tw_log2) + lx;
+            const int y = (ty << p.th_log2) + ly;
+            const int n = (tn << (7 - p.tw_log2 - p.th_log2)) + ln;
+            const bool live = (n < p.B) && (y < p.H) && (x < p.W);
+
+            mbar_wait(&tfull_bar[acc], acc_ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+            const float* bias_t = sbias + n_tile * BLOCK_N;
+
+            if constexpr (MODE == MODE_HEAD) {
+                static_assert(MODE != MODE_HEAD || BLOCK_N == kHeadIn, "head wants all channels of a pixel");
+                float o[kHeadOut];
+#pragma unroll
+                for (int k = 0; k < kHeadOut; ++k) o[k] = p.head.b[k];
+#pragma unroll
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float h = fmaxf(__uint_as_float(r[j]) + bias_t[c * 32 + j], 0.f);
+#pragma unroll
+                        for (int k = 0; k < kHeadOut; ++k) o[k] = fmaf(h, p.head.w[k * kHeadIn + c * 32 + j], o[k]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // accumulator drained: MMAs of tile+2 may start
+
+                if (live) {
+                    const StepCoef& sc = p.head.step;
+                    const size_t plane = static_cast<size_t>(p.H) * p.W;
+                    const size_t pix = static_cast<size_t>(y) * p.W + x;
+                    float res[kHeadOut];
+#pragma unroll
+                    for (int k = 0; k < kHeadOut; ++k) {
+                        const size_t idx = (static_cast<size_t>(n) * kHeadOut + k) * plane + pix;
+                        const float pr = o[k];
+                        if (p.head.pred_out != nullptr) p.head.pred_out[idx] = pr;
+                        res[k] = pr;
+                        if (sc.kind != STEP_NONE) {
+                            const float xt = p.head.x_t[idx];
+                            float x0 = 0.f, e = pr, xn;
+                            if (sc.kind == STEP_EPS_DDIM) {
+                                x0 = __fdiv_rn(__fsub_rn(xt, __fmul_rn(sc.c0, pr)), sc.c1);
+                            } else if (sc.kind == STEP_V_DDIM || sc.kind == STEP_V_DDPM) {
+                                x0 = __fsub_rn(__fmul_rn(sc.c0, xt), __fmul_rn(sc.c1, pr));
+                                e = __fadd_rn(__fmul_rn(sc.c1, xt), __fmul_rn(sc.c0, pr));
+                            }
+                            const bool ddpm = sc.kind == STEP_EPS_DDPM || sc.kind == STEP_V_DDPM;
+                            if (ddpm) xn = __fmul_rn(sc.c2, __fsub_rn(xt, __fmul_rn(sc.c3, e)));
+                            else      xn = __fadd_rn(__fmul_rn(sc.c2, x0), __fmul_rn(sc.c3, e));
+                            if (sc.flags & STEP_FLAG_NOISE) xn = __fadd_rn(xn, __fmul_rn(sc.c4, p.head.noise[idx]));
+                            if (sc.flags & STEP_FLAG_FINAL) xn = fminf(fmaxf(ddpm ? xn : x0, 0.f), 1.f);
+                            p.head.x_t[idx] = xn;
+                            res[k] = xn;
+                        }
+                    }
+                    if (sc.kind != STEP_NONE && p.head.xin16 != nullptr) {
+                        uint4 v;
+                        v.x = pack_half2_sat(res[0], res[1]);
+                        v.y = pack_half2_sat(res[2], res[3]);
+                        v.z = pack_half2_sat(sc.t_next, sc.t_next);
+                        v.w = 0u;
+                        *reinterpret_cast<uint4*>(p.head.xin16 + ((static_cast<size_t>(n) * p.H + y) * p.W + x) * 16) = v;
+                    }
+                }
+            } else {
+                // destination pixel row (channel 0 of this N tile / tap), resolved per chunk for CONVT
+                __half* dst_px = nullptr;
+                bool writer = live;
+                if constexpr (MODE == MODE_STORE) {
+                    dst_px = p.out + ((static_cast<size_t>(n) * p.H + y) * p.W + x) * p.out_cpitch + n_tile * BLOCK_N;
+                } else if constexpr (MODE == MODE_POOL) {
+                    writer = live && ((lx | ly) & 1) == 0;
+                    dst_px = p.out + ((static_cast<size_t>(n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.out_cpitch +
+                             n_tile * BLOCK_N;
+                }
+#pragma unroll
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    uint32_t h[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = __uint_as_float(r[2 * j]) + bias_t[c * 32 + 2 * j];
+                        float b = __uint_as_float(r[2 * j + 1]) + bias_t[c * 32 + 2 * j + 1];
+                        if constexpr (MODE != MODE_CONVT) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                        h[j] = pack_half2_sat(a, b);
+                    }
+                    __half* dst;
+                    if constexpr (MODE == MODE_POOL) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            h[j] = hmax2_u32(h[j], __shfl_xor_sync(0xffffffffu, h[j], 1));
+                            h[j] = hmax2_u32(h[j], __shfl_xor_sync(0xffffffffu, h[j], tw));
+                        }
+                        dst = dst_px + c * 32;
+                    } else if constexpr (MODE == MODE_CONVT) {
+                        const int ng = n_tile * BLOCK_N + c * 32;
+                        const int tap = ng / p.cout;
+                        const int co = ng - tap * p.cout;
+                        const int oy = 2 * y + (tap >> 1), ox = 2 * x + (tap & 1);
+                        dst = p.out + ((static_cast<size_t>(n) * (2 * p.H) + oy) * (2 * p.W) + ox) * p.out_cpitch + co;
+                    } else {
+                        dst = dst_px + c * 32;
+                    }
+                    if (writer) {
+                        uint4* d4 = reinterpret_cast<uint4*>(dst);
+                        d4[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                        d4[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                        d4[2] = make_uint4(h[8], h[9], h[10], h[11]);
+                        d4[3] = make_uint4(h[12], h[13], h[14], h[15]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
+            acc ^= 1;
+            if (acc == 0) acc_ph ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace s1s2

@@ -1,0 +1,745 @@
+// libs1s2_b200.so -- host side of the C ABI declared in include/s1s2_b200.h.
+//
+// Owns: the fp16 NHWC activation arena, the repacked fp16 weights, one TMA tensor map pair per convolution and
+// the launch sequence of the denoiser (16 launches per model call: 13 3x3 convs, 3 transposed convs; the 1x1
+// head and the scheduler update ride in the last conv's epilogue).  sm_100a only, no CPU fallback: s1s2_create
+// fails on anything that is not a compute-capability-10.x device.
+//
+// Reference semantics: UNetSmall.forward (Evaluation/DDIM_Multi-step.py:42-53) and the sampler loops listed in
+// the header.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/s1s2_b200.h"
+#include "conv_umma.cuh"
+#include "patch_kernels.cuh"
+
+using namespace s1s2;
+
+namespace {
+
+thread_local std::string g_error;
+
+void set_err(std::string* dst, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    *dst = buf;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            set_err(err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return S1S2_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------- small kernels
+// Input assembly (replaces t_idx.view.float.repeat + 2x torch.cat, DDIM_Multi-step.py:44-45,131):
+// NCHW f32 -> NHWC16 fp16 pixel record [x0 x1 x2 x3 | t t 0 0 | c0 c1 c2 c3 | 0 0 0 0].  The timestep rides in two
+// planes because its weight is split into an fp16 hi/lo pair (exact t up to 2048, weight error 2^-22 instead of 2^-11).
+__global__ void pack_input_kernel(const float* __restrict__ x, size_t x_bstride, const float* __restrict__ cond,
+                                  size_t c_bstride, const int64_t* __restrict__ t_idx, float t_const, float scale,
+                                  float* __restrict__ state, __half* __restrict__ xin16, int HW, size_t total) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= total) return;
+    const int b = static_cast<int>(i / HW);
+    const int pix = static_cast<int>(i - static_cast<size_t>(b) * HW);
+    const float t = t_idx != nullptr ? static_cast<float>(t_idx[b]) : t_const;
+    float xv[4], cv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        xv[k] = __fmul_rn(x[b * x_bstride + static_cast<size_t>(k) * HW + pix], scale);
+        cv[k] = cond[b * c_bstride + static_cast<size_t>(k) * HW + pix];
+        if (state != nullptr) state[(static_cast<size_t>(b) * 4 + k) * HW + pix] = xv[k];
+    }
+    uint4 lo, hi;
+    lo.x = pack_half2_sat(xv[0], xv[1]);
+    lo.y = pack_half2_sat(xv[2], xv[3]);
+    lo.z = pack_half2_sat(t, t);
+    lo.w = 0u;
+    hi.x = pack_half2_sat(cv[0], cv[1]);
+    hi.y = pack_half2_sat(cv[2], cv[3]);
+    hi.z = 0u;
+    hi.w = 0u;
+    uint4* dst = reinterpret_cast<uint4*>(xin16 + i * 16);
+    dst[0] = lo;
+    dst[1] = hi;
+}
+
+// Conv2d weight OIHW f32 -> [cout][tap][cin] fp16 (K-major rows for the UMMA B operand).
+__global__ void repack_conv3_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin) {
+    const size_t n = static_cast<size_t>(cout) * 9 * cin;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % cin);
+        const int tap = static_cast<int>((i / cin) % 9);
+        const int co = static_cast<int>(i / (static_cast<size_t>(cin) * 9));
+        out[i] = __float2half_rn(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap]);
+    }
+}
+// inc.0.weight [cout][9][3][3] -> [cout][tap][16] in the pixel-record order of pack_input_kernel.
+__global__ void repack_inc_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout) {
+    const int n = cout * 9 * 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int slot = i % 16;
+        const int tap = (i / 16) % 9;
+        const int co = i / (16 * 9);
+        auto W = [&](int ci) { return w[(static_cast<size_t>(co) * 9 + ci) * 9 + tap]; };
+        float v = 0.f;
+        if (slot < 4) v = W(slot);                       // x_t
+        else if (slot == 4) v = __half2float(__float2half_rn(W(8)));                               // t, hi part
+        else if (slot == 5) v = W(8) - __half2float(__float2half_rn(W(8)));                        // t, lo part
+        else if (slot >= 8 && slot < 12) v = W(4 + slot - 8);                                      // cond
+        out[i] = __float2half_rn(v);
+    }
+}
+// ConvTranspose2d weight IOHW f32 [cin][cout][2][2] -> [(ky*2+kx)*cout + co][cin] fp16.
+__global__ void repack_convt_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout) {
+    const size_t n = static_cast<size_t>(4) * cout * cin;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % cin);
+        const int co = static_cast<int>((i / cin) % cout);
+        const int tap = static_cast<int>(i / (static_cast<size_t>(cin) * cout));
+        out[i] = __float2half_rn(w[(static_cast<size_t>(ci) * cout + co) * 4 + tap]);
+    }
+}
+__global__ void tile_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int cout, int reps) {
+    const int n = cout * reps;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = b[i % cout];
+}
+// Debug / per-layer parity tap: NHWC fp16 view -> NCHW f32.
+__global__ void unpack_activation_kernel(const __half* __restrict__ src, int cpitch, int C, int HW, float* __restrict__ out,
+                                         size_t total) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;   // over B*C*HW, NCHW order
+    if (i >= total) return;
+    const int pix = static_cast<int>(i % HW);
+    const int c = static_cast<int>((i / HW) % C);
+    const size_t b = i / (static_cast<size_t>(HW) * C);
+    out[i] = __half2float(src[(b * HW + pix) * cpitch + c]);
+}
+
+// ---------------------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int kbox) {
+    return kbox == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// ---------------------------------------------------------------------------------------------- layers
+enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_N96, K_HEAD, K_COUNT };
+
+struct KernelInfo {
+    void (*fn)(const ConvParams);
+    int block_n, kbox, boxes, smem;
+};
+
+template <int BN, int KB, int BX, int ST, int MODE>
+KernelInfo make_kernel() {
+    KernelInfo k;
+    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE>;
+    k.block_n = BN;
+    k.kbox = KB;
+    k.boxes = BX;
+    k.smem = ConvSmem<BN, KB, BX, ST>::kBytes;
+    return k;
+}
+
+const KernelInfo* kernel_table() {
+    static KernelInfo t[K_COUNT];
+    static bool init = false;
+    if (!init) {
+        t[K_INC] = make_kernel<96, 16, 3, 4, MODE_STORE>();     // Cin = 16-channel pixel record
+        t[K_C96IN] = make_kernel<192, 32, 3, 3, MODE_STORE>();  // Cin = 96 (64-byte swizzle rows)
+        t[K_STORE] = make_kernel<192, 64, 1, 5, MODE_STORE>();
+        t[K_POOL] = make_kernel<192, 64, 1, 5, MODE_POOL>();
+        t[K_CONVT] = make_kernel<192, 64, 1, 5, MODE_CONVT>();
+        t[K_N96] = make_kernel<96, 64, 1, 7, MODE_STORE>();     // Cout = 96
+        t[K_HEAD] = make_kernel<96, 32, 3, 5, MODE_HEAD>();     // conv1.2 + outc + scheduler
+        init = true;
+    }
+    return t;
+}
+
+struct Layer {
+    const char* name;        // state_dict prefix
+    KernelId kid;
+    int level;               // input resolution = (H >> level, W >> level)
+    int cin;                 // K per tap (padded for inc)
+    int ntot;                // GEMM N (CONVT: 4 * cout)
+    int cout;                // real output channels per pixel
+    int taps_w;
+    const __half* src;       // input view
+    int src_pitch;
+    __half* dst;             // output view (channel offset applied)
+    int dst_pitch;
+    __half* w = nullptr;
+    float* bias = nullptr;
+    ConvParams p;
+};
+
+struct View {
+    const char* name;
+    const __half* ptr;
+    int pitch, C, level;
+};
+
+}  // namespace
+
+struct s1s2_handle {
+    int device = 0;
+    int H = 0, W = 0, max_batch = 0, nalloc = 0;
+    int num_sms = 0;
+    bool weights_loaded = false;
+    std::string err;
+    int64_t launches = 0;
+    std::vector<void*> allocs;
+    std::vector<Layer> layers;
+    std::vector<View> views;
+    __half* xin16 = nullptr;
+    float head_w[kHeadOut * kHeadIn];
+    float head_b[kHeadOut];
+    // staging for s1s2_sample_host
+    float *st_cond = nullptr, *st_x = nullptr, *st_out = nullptr;
+};
+
+namespace {
+
+struct TileGeom {
+    int tw_log2, th_log2, tn, tiles_x, tiles_y;
+};
+
+int ilog2(int v) {
+    int l = 0;
+    while ((1 << (l + 1)) <= v) ++l;
+    return l;
+}
+
+TileGeom tile_geom(int Hl, int Wl) {
+    TileGeom g;
+    int tw = Wl & -Wl;
+    if (tw > 16) tw = 16;
+    int th = 1 << ilog2(Hl);
+    if (th > 128 / tw) th = 128 / tw;
+    g.tw_log2 = ilog2(tw);
+    g.th_log2 = ilog2(th);
+    g.tn = 128 / (tw * th);
+    g.tiles_x = Wl / tw;
+    g.tiles_y = (Hl + th - 1) / th;
+    return g;
+}
+
+int dmalloc(s1s2_handle* h, void** p, size_t bytes, std::string* err) {
+    CK(cudaMalloc(p, bytes));
+    h->allocs.push_back(*p);
+    return S1S2_OK;
+}
+
+int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
+    const KernelInfo& k = kernel_table()[L.kid];
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) {
+        set_err(err, "cuTensorMapEncodeTiled is not available from this driver");
+        return S1S2_ERR_CUDA;
+    }
+    const int Hl = h->H >> L.level, Wl = h->W >> L.level;
+    const TileGeom g = tile_geom(Hl, Wl);
+    if (L.cin % k.kbox != 0 || (L.taps_w * L.taps_w * (L.cin / k.kbox)) % k.boxes != 0 || L.ntot % k.block_n != 0) {
+        set_err(err, "layer %s: geometry does not fit kernel (cin %d, N %d)", L.name, L.cin, L.ntot);
+        return S1S2_ERR_INVALID;
+    }
+    ConvParams& p = L.p;
+    memset(&p, 0, sizeof(p));
+    {   // activations: (C, W, H, N), box (kbox, tw, th, tn)
+        cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cin), static_cast<cuuint64_t>(Wl), static_cast<cuuint64_t>(Hl),
+                              static_cast<cuuint64_t>(h->nalloc)};
+        cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.src_pitch) * 2, static_cast<cuuint64_t>(Wl) * L.src_pitch * 2,
+                                 static_cast<cuuint64_t>(Hl) * Wl * L.src_pitch * 2};
+        cuuint32_t box[4] = {static_cast<cuuint32_t>(k.kbox), 1u << g.tw_log2, 1u << g.th_log2,
+                             static_cast<cuuint32_t>(g.tn)};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&p.tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(L.src), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(k.kbox), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_err(err, "layer %s: activation tensor map rejected (CUresult %d)", L.name, static_cast<int>(r));
+            return S1S2_ERR_CUDA;
+        }
+    }
+    {   // weights: (K, N), box (kbox, block_n)
+        const int ktot = L.taps_w * L.taps_w * L.cin;
+        cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(L.ntot)};
+        cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(k.kbox), static_cast<cuuint32_t>(k.block_n)};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&p.tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L.w, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(k.kbox), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_err(err, "layer %s: weight tensor map rejected (CUresult %d)", L.name, static_cast<int>(r));
+            return S1S2_ERR_CUDA;
+        }
+    }
+    p.bias = L.bias;
+    p.out = L.dst;
+    p.out_cpitch = L.dst_pitch;
+    p.H = Hl;
+    p.W = Wl;
+    p.B = 0;
+    p.tw_log2 = g.tw_log2;
+    p.th_log2 = g.th_log2;
+    p.tiles_x = g.tiles_x;
+    p.tiles_y = g.tiles_y;
+    p.num_m_tiles = 0;
+    p.num_n_tiles = L.ntot / k.block_n;
+    p.taps_w = L.taps_w;
+    p.chunks = L.cin / k.kbox;
+    p.cout = L.cout;
+    return S1S2_OK;
+}
+
+int launch_layer(s1s2_handle* h, Layer& L, int B, cudaStream_t st, std::string* err) {
+    const KernelInfo& k = kernel_table()[L.kid];
+    ConvParams& p = L.p;
+    const int tn = 128 >> (p.tw_log2 + p.th_log2);
+    p.B = B;
+    p.num_m_tiles = p.tiles_x * p.tiles_y * ((B + tn - 1) / tn);
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    k.fn<<<grid, 256, k.smem, st>>>(p);
+    CK(cudaGetLastError());
+    ++h->launches;
+    return S1S2_OK;
+}
+
+int run_network(s1s2_handle* h, int B, const HeadParams& head_io, cudaStream_t st, std::string* err) {
+    for (size_t i = 0; i < h->layers.size(); ++i) {
+        Layer& L = h->layers[i];
+        if (L.kid == K_HEAD) {
+            HeadParams& hp = L.p.head;
+            memcpy(hp.w, h->head_w, sizeof(hp.w));
+            memcpy(hp.b, h->head_b, sizeof(hp.b));
+            hp.x_t = head_io.x_t;
+            hp.pred_out = head_io.pred_out;
+            hp.noise = head_io.noise;
+            hp.xin16 = head_io.xin16;
+            hp.step = head_io.step;
+        }
+        int rc = launch_layer(h, L, B, st, err);
+        if (rc != S1S2_OK) return rc;
+    }
+    return S1S2_OK;
+}
+
+int check_batch(s1s2_handle* h, int B) {
+    if (h == nullptr) return S1S2_ERR_INVALID;
+    if (!h->weights_loaded) {
+        h->err = "weights not loaded: call s1s2_load_weights first";
+        return S1S2_ERR_STATE;
+    }
+    if (B < 1 || B > h->max_batch) {
+        set_err(&h->err, "batch %d outside [1, max_batch=%d]", B, h->max_batch);
+        return S1S2_ERR_INVALID;
+    }
+    return S1S2_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int s1s2_abi_version(void) { return 1; }
+
+const char* s1s2_global_error(void) { return g_error.c_str(); }
+const char* s1s2_last_error(const s1s2_handle* h) { return h != nullptr ? h->err.c_str() : g_error.c_str(); }
+int64_t s1s2_launch_count(const s1s2_handle* h) { return h != nullptr ? h->launches : 0; }
+
+int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_ch, int H, int W, int max_batch) {
+    std::string* err = &g_error;
+    if (out == nullptr) return S1S2_ERR_INVALID;
+    *out = nullptr;
+    if (in_ch != 8 || out_ch != 4 || base_ch != 96) {
+        set_err(err, "unsupported architecture (in_ch %d, out_ch %d, base_ch %d): this library implements "
+                     "UNetSmall(8, 4, 96)", in_ch, out_ch, base_ch);
+        return S1S2_ERR_INVALID;
+    }
+    if (H < 16 || W < 16 || H % 16 != 0 || W % 16 != 0 || max_batch < 1) {
+        set_err(err, "H and W must be multiples of 16 (got %d x %d), max_batch >= 1 (got %d)", H, W, max_batch);
+        return S1S2_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        set_err(err, "no CUDA device %d (found %d); this library has no CPU fallback", device, ndev);
+        return S1S2_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_err(err, "device %d is sm_%d%d; libs1s2_b200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return S1S2_ERR_CUDA;
+    }
+    CK(cudaSetDevice(device));
+    s1s2_handle* h = new s1s2_handle();
+    h->device = device;
+    h->H = H;
+    h->W = W;
+    h->max_batch = max_batch;
+    h->num_sms = prop.multiProcessorCount;
+    const int tn_max = tile_geom(H >> 3, W >> 3).tn;   // coarsest level packs the most images into one M tile
+    h->nalloc = ((max_batch + tn_max - 1) / tn_max) * tn_max;
+
+    const KernelInfo* kt = kernel_table();
+    for (int i = 0; i < K_COUNT; ++i) {
+        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kt[i].fn),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kt[i].smem);
+        if (e != cudaSuccess) {
+            set_err(err, "cudaFuncSetAttribute(kernel %d, %d B smem): %s", i, kt[i].smem, cudaGetErrorString(e));
+            delete h;
+            return S1S2_ERR_CUDA;
+        }
+    }
+
+    const size_t N = static_cast<size_t>(h->nalloc);
+    const size_t P0 = static_cast<size_t>(H) * W, P1 = P0 / 4, P2 = P0 / 16, P3 = P0 / 64;
+    __half *cat1, *d1a, *cat2, *d2a, *cat3, *d3a, *e4, *c3a, *c3b, *c2a, *c2b, *c1a;
+    struct { __half** p; size_t elems; } bufs[] = {
+        {&h->xin16, N * P0 * 16}, {&cat1, N * P0 * 192}, {&d1a, N * P0 * 192}, {&cat2, N * P1 * 384},
+        {&d2a, N * P1 * 384},     {&cat3, N * P2 * 768}, {&d3a, N * P2 * 768}, {&e4, N * P3 * 768},
+        {&c3a, N * P2 * 384},     {&c3b, N * P2 * 384},  {&c2a, N * P1 * 192}, {&c2b, N * P1 * 192},
+        {&c1a, N * P0 * 96}};
+    for (auto& b : bufs) {
+        void* p = nullptr;
+        if (dmalloc(h, &p, b.elems * sizeof(__half), err) != S1S2_OK) {
+            s1s2_destroy(h);
+            return S1S2_ERR_CUDA;
+        }
+        cudaMemset(p, 0, b.elems * sizeof(__half));
+        *b.p = static_cast<__half*>(p);
+    }
+    {
+        const size_t img = static_cast<size_t>(max_batch) * 4 * P0 * sizeof(float);
+        void* p;
+        if (dmalloc(h, &p, img, err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
+        h->st_cond = static_cast<float*>(p);
+        if (dmalloc(h, &p, img, err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
+        h->st_x = static_cast<float*>(p);
+        if (dmalloc(h, &p, img, err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
+        h->st_out = static_cast<float*>(p);
+    }
+
+    auto add = [&](const char* name, KernelId kid, int level, int cin, int ntot, int cout, int taps, const __half* src,
+                   int sp, __half* dst, int dp) {
+        Layer L;
+        L.name = name; L.kid = kid; L.level = level; L.cin = cin; L.ntot = ntot; L.cout = cout; L.taps_w = taps;
+        L.src = src; L.src_pitch = sp; L.dst = dst; L.dst_pitch = dp;
+        h->layers.push_back(L);
+    };
+    //   name          kernel    lvl cin  N     cout taps src          pitch dst           pitch
+    add("inc.0",       K_INC,    0,  16,  96,   96,  3,   h->xin16,    16,   cat1 + 96,    192);
+    add("down1.0.0",   K_C96IN,  0,  96,  192,  192, 3,   cat1 + 96,   192,  d1a,          192);
+    add("down1.0.2",   K_POOL,   0,  192, 192,  192, 3,   d1a,         192,  cat2 + 192,   384);
+    add("down2.0.0",   K_STORE,  1,  192, 384,  384, 3,   cat2 + 192,  384,  d2a,          384);
+    add("down2.0.2",   K_POOL,   1,  384, 384,  384, 3,   d2a,         384,  cat3 + 384,   768);
+    add("down3.0.0",   K_STORE,  2,  384, 768,  768, 3,   cat3 + 384,  768,  d3a,          768);
+    add("down3.0.2",   K_POOL,   2,  768, 768,  768, 3,   d3a,         768,  e4,           768);
+    add("up3",         K_CONVT,  3,  768, 1536, 384, 1,   e4,          768,  cat3,         768);
+    add("conv3.0",     K_STORE,  2,  768, 384,  384, 3,   cat3,        768,  c3a,          384);
+    add("conv3.2",     K_STORE,  2,  384, 384,  384, 3,   c3a,         384,  c3b,          384);
+    add("up2",         K_CONVT,  2,  384, 768,  192, 1,   c3b,         384,  cat2,         384);
+    add("conv2.0",     K_STORE,  1,  384, 192,  192, 3,   cat2,        384,  c2a,          192);
+    add("conv2.2",     K_STORE,  1,  192, 192,  192, 3,   c2a,         192,  c2b,          192);
+    add("up1",         K_CONVT,  1,  192, 384,  96,  1,   c2b,         192,  cat1,         192);
+    add("conv1.0",     K_N96,    0,  192, 96,   96,  3,   cat1,        192,  c1a,          96);
+    add("conv1.2",     K_HEAD,   0,  96,  96,   96,  3,   c1a,         96,   nullptr,      0);
+
+    for (Layer& L : h->layers) {
+        const size_t welems = static_cast<size_t>(L.ntot) * L.taps_w * L.taps_w * L.cin;
+        void* p;
+        if (dmalloc(h, &p, welems * sizeof(__half), err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
+        L.w = static_cast<__half*>(p);
+        if (dmalloc(h, &p, static_cast<size_t>(L.ntot) * sizeof(float), err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
+        L.bias = static_cast<float*>(p);
+        int rc = build_layer_params(h, L, err);
+        if (rc != S1S2_OK) { s1s2_destroy(h); return rc; }
+    }
+    // views for s1s2_debug_activation: name = the oracle's tap key
+    h->views = {{"inc", cat1 + 96, 192, 96, 0},      {"down1.0", d1a, 192, 192, 0}, {"down1", cat2 + 192, 384, 192, 1},
+                {"down2.0", d2a, 384, 384, 1},       {"down2", cat3 + 384, 768, 384, 2}, {"down3.0", d3a, 768, 768, 2},
+                {"down3", e4, 768, 768, 3},          {"up3", cat3, 768, 384, 2},    {"conv3.0", c3a, 384, 384, 2},
+                {"conv3", c3b, 384, 384, 2},         {"up2", cat2, 384, 192, 1},    {"conv2.0", c2a, 192, 192, 1},
+                {"conv2", c2b, 192, 192, 1},         {"up1", cat1, 192, 96, 0},     {"conv1.0", c1a, 96, 96, 0},
+                {"xin16", h->xin16, 16, 16, 0}};
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        set_err(err, "arena initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        s1s2_destroy(h);
+        return S1S2_ERR_CUDA;
+    }
+    *out = h;
+    return S1S2_OK;
+}
+
+void s1s2_destroy(s1s2_handle* h) {
+    if (h == nullptr) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+}
+
+int s1s2_load_weights(s1s2_handle* h, int n, const char* const* names, const float* const* ptrs, const int64_t* numel,
+                      void* stream) {
+    if (h == nullptr) return S1S2_ERR_INVALID;
+    std::string* err = &h->err;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    auto find = [&](const std::string& key, int64_t want, const float** out) -> int {
+        for (int i = 0; i < n; ++i) {
+            if (key == names[i]) {
+                if (numel[i] != want) {
+                    set_err(err, "size mismatch for %s: got %lld elements, expected %lld", key.c_str(),
+                            static_cast<long long>(numel[i]), static_cast<long long>(want));
+                    return S1S2_ERR_INVALID;
+                }
+                *out = ptrs[i];
+                return S1S2_OK;
+            }
+        }
+        set_err(err, "missing key in state_dict: %s", key.c_str());
+        return S1S2_ERR_INVALID;
+    };
+    if (n != 34) {
+        set_err(err, "strict load: expected the 34 tensors of UNetSmall(8,4,96), got %d", n);
+        return S1S2_ERR_INVALID;
+    }
+    for (Layer& L : h->layers) {
+        const float *w = nullptr, *b = nullptr;
+        const std::string nm = L.name;
+        int rc;
+        if (L.kid == K_INC) {
+            if ((rc = find(nm + ".weight", 96 * 9 * 9, &w)) || (rc = find(nm + ".bias", 96, &b))) return rc;
+            repack_inc_kernel<<<64, 256, 0, st>>>(w, L.w, 96);
+            tile_bias_kernel<<<4, 256, 0, st>>>(b, L.bias, 96, 1);
+        } else if (L.kid == K_CONVT) {
+            if ((rc = find(nm + ".weight", static_cast<int64_t>(L.cin) * L.cout * 4, &w)) ||
+                (rc = find(nm + ".bias", L.cout, &b)))
+                return rc;
+            repack_convt_kernel<<<512, 256, 0, st>>>(w, L.w, L.cin, L.cout);
+            tile_bias_kernel<<<8, 256, 0, st>>>(b, L.bias, L.cout, 4);
+        } else {
+            if ((rc = find(nm + ".weight", static_cast<int64_t>(L.cout) * L.cin * 9, &w)) ||
+                (rc = find(nm + ".bias", L.cout, &b)))
+                return rc;
+            repack_conv3_kernel<<<1024, 256, 0, st>>>(w, L.w, L.cout, L.cin);
+            tile_bias_kernel<<<8, 256, 0, st>>>(b, L.bias, L.cout, 1);
+        }
+        h->launches += 2;
+        CK(cudaGetLastError());
+    }
+    {
+        const float *w = nullptr, *b = nullptr;
+        int rc;
+        if ((rc = find("outc.weight", kHeadOut * kHeadIn, &w)) || (rc = find("outc.bias", kHeadOut, &b))) return rc;
+        CK(cudaMemcpyAsync(h->head_w, w, sizeof(h->head_w), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->head_b, b, sizeof(h->head_b), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    h->weights_loaded = true;
+    return S1S2_OK;
+}
+
+int s1s2_forward(s1s2_handle* h, const float* xt_and_cond, const int64_t* t_idx, float* out, int B, void* stream) {
+    int rc = check_batch(h, B);
+    if (rc != S1S2_OK) return rc;
+    std::string* err = &h->err;
+    if (xt_and_cond == nullptr || t_idx == nullptr || out == nullptr) {
+        h->err = "s1s2_forward: null pointer argument";
+        return S1S2_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const int HW = h->H * h->W;
+    const size_t total = static_cast<size_t>(B) * HW;
+    pack_input_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+        xt_and_cond, static_cast<size_t>(8) * HW, xt_and_cond + static_cast<size_t>(4) * HW, static_cast<size_t>(8) * HW,
+        t_idx, 0.f, 1.f, nullptr, h->xin16, HW, total);
+    CK(cudaGetLastError());
+    ++h->launches;
+    HeadParams io;
+    memset(&io, 0, sizeof(io));
+    io.pred_out = out;
+    io.step.kind = STEP_NONE;
+    return run_network(h, B, io, st, err);
+}
+
+int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond, const float* x_init,
+                float init_scale, const float* step_noise, float* out, float* tap_pred, float* tap_x, int B,
+                void* stream) {
+    int rc = check_batch(h, B);
+    if (rc != S1S2_OK) return rc;
+    std::string* err = &h->err;
+    if (steps == nullptr || n_steps < 1 || cond == nullptr || x_init == nullptr || out == nullptr) {
+        h->err = "s1s2_sample: null pointer / empty step list";
+        return S1S2_ERR_INVALID;
+    }
+    for (int i = 0; i < n_steps; ++i) {
+        if (steps[i].t < 0 || steps[i].t > 2048) {
+            set_err(err, "step %d: timestep %d outside [0, 2048] (fp16-exact range of the time planes)", i, steps[i].t);
+            return S1S2_ERR_INVALID;
+        }
+        if (steps[i].kind < S1S2_STEP_EPS_DDIM || steps[i].kind > S1S2_STEP_V_DDPM) {
+            set_err(err, "step %d: unknown scheduler kind %d", i, steps[i].kind);
+            return S1S2_ERR_INVALID;
+        }
+        if ((steps[i].flags & S1S2_STEP_NOISE) && (step_noise == nullptr || steps[i].noise_index < 0)) {
+            set_err(err, "step %d asks for noise but step_noise is NULL / noise_index < 0", i);
+            return S1S2_ERR_INVALID;
+        }
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const int HW = h->H * h->W;
+    const size_t total = static_cast<size_t>(B) * HW;
+    const size_t img = static_cast<size_t>(B) * 4 * HW;
+    pack_input_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+        x_init, static_cast<size_t>(4) * HW, cond, static_cast<size_t>(4) * HW, nullptr, static_cast<float>(steps[0].t),
+        init_scale, out, h->xin16, HW, total);
+    CK(cudaGetLastError());
+    ++h->launches;
+    for (int i = 0; i < n_steps; ++i) {
+        HeadParams io;
+        memset(&io, 0, sizeof(io));
+        io.x_t = out;
+        io.pred_out = tap_pred != nullptr ? tap_pred + static_cast<size_t>(i) * img : nullptr;
+        io.noise = (steps[i].flags & S1S2_STEP_NOISE) ? step_noise + static_cast<size_t>(steps[i].noise_index) * img : nullptr;
+        io.xin16 = h->xin16;
+        io.step.c0 = steps[i].c0;
+        io.step.c1 = steps[i].c1;
+        io.step.c2 = steps[i].c2;
+        io.step.c3 = steps[i].c3;
+        io.step.c4 = steps[i].c4;
+        io.step.t_next = i + 1 < n_steps ? static_cast<float>(steps[i + 1].t) : 0.f;
+        io.step.kind = steps[i].kind;
+        io.step.flags = steps[i].flags;
+        rc = run_network(h, B, io, st, err);
+        if (rc != S1S2_OK) return rc;
+        if (tap_x != nullptr)
+            CK(cudaMemcpyAsync(tap_x + static_cast<size_t>(i) * img, out, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    return S1S2_OK;
+}
+
+int s1s2_sample_host(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond_host,
+                     const float* x_init_host, float init_scale, float* out_host, int B, void* stream) {
+    int rc = check_batch(h, B);
+    if (rc != S1S2_OK) return rc;
+    std::string* err = &h->err;
+    if (cond_host == nullptr || x_init_host == nullptr || out_host == nullptr) {
+        h->err = "s1s2_sample_host: null pointer argument";
+        return S1S2_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = static_cast<size_t>(B) * 4 * h->H * h->W * sizeof(float);
+    CK(cudaMemcpyAsync(h->st_cond, cond_host, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->st_x, x_init_host, bytes, cudaMemcpyHostToDevice, st));
+    rc = s1s2_sample(h, steps, n_steps, h->st_cond, h->st_x, init_scale, nullptr, h->st_out, nullptr, nullptr, B, stream);
+    if (rc != S1S2_OK) return rc;
+    CK(cudaMemcpyAsync(out_host, h->st_out, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S1S2_OK;
+}
+
+int s1s2_debug_activation(s1s2_handle* h, const char* name, float* out_nchw, int B, int* C, int* Hout, int* Wout,
+                          void* stream) {
+    if (h == nullptr || name == nullptr) return S1S2_ERR_INVALID;
+    std::string* err = &h->err;
+    for (const View& v : h->views) {
+        if (strcmp(v.name, name) == 0) {
+            const int Hl = h->H >> v.level, Wl = h->W >> v.level;
+            if (C != nullptr) *C = v.C;
+            if (Hout != nullptr) *Hout = Hl;
+            if (Wout != nullptr) *Wout = Wl;
+            if (out_nchw == nullptr) return S1S2_OK;   // shape query
+            if (B < 1 || B > h->max_batch) return S1S2_ERR_INVALID;
+            CK(cudaSetDevice(h->device));
+            const size_t total = static_cast<size_t>(B) * v.C * Hl * Wl;
+            unpack_activation_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                v.ptr, v.pitch, v.C, Hl * Wl, out_nchw, total);
+            CK(cudaGetLastError());
+            ++h->launches;
+            return S1S2_OK;
+        }
+    }
+    set_err(err, "unknown activation '%s'", name);
+    return S1S2_ERR_INVALID;
+}
+
+int s1s2_tile_extract(int device, const float* scene, const uint8_t* vmask, int SH, int SW, const int32_t* origins, int N,
+                      int ps, float* cond, uint8_t* mask, float* valid_ratio, void* stream) {
+    std::string* err = &g_error;
+    if (scene == nullptr || origins == nullptr || cond == nullptr || mask == nullptr || N < 0 || ps < 1 || ps > SH || ps > SW) {
+        set_err(err, "s1s2_tile_extract: bad argument (N %d, ps %d, scene %d x %d)", N, ps, SH, SW);
+        return S1S2_ERR_INVALID;
+    }
+    if (N == 0) return S1S2_OK;
+    CK(cudaSetDevice(device));
+    tile_extract_kernel<<<N, kExtractThreads, 0, static_cast<cudaStream_t>(stream)>>>(scene, vmask, SH, SW, origins, ps, cond,
+                                                                                     mask, valid_ratio);
+    CK(cudaGetLastError());
+    return S1S2_OK;
+}
+
+int s1s2_stitch(int device, const float* preds, const int32_t* origins, int N, int C, int ps, int stride, int SH, int SW,
+                float* canvas, uint8_t* cover, void* stream) {
+    std::string* err = &g_error;
+    if (preds == nullptr || origins == nullptr || canvas == nullptr || cover == nullptr || N < 0 || C < 1 || C > kStitchMaxC ||
+        ps < 1 || stride < 1 || ps > SH || ps > SW) {
+        set_err(err, "s1s2_stitch: bad argument (N %d, C %d, ps %d, stride %d, scene %d x %d)", N, C, ps, stride, SH, SW);
+        return S1S2_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(device));
+    const int nrows = (SH - ps) / stride + 1, ncols = (SW - ps) / stride + 1;
+    int32_t* grid_map = nullptr;
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&grid_map), sizeof(int32_t) * nrows * ncols, st));
+    CK(cudaMemsetAsync(grid_map, 0xFF, sizeof(int32_t) * nrows * ncols, st));
+    if (N > 0) {
+        stitch_map_kernel<<<(N + 255) / 256, 256, 0, st>>>(origins, N, stride, nrows, ncols, grid_map);
+        CK(cudaGetLastError());
+    }
+    dim3 grid((SW + 127) / 128, SH);
+    stitch_gather_kernel<<<grid, 128, 0, st>>>(preds, grid_map, C, ps, stride, nrows, ncols, SH, SW, canvas, cover);
+    CK(cudaGetLastError());
+    CK(cudaFreeAsync(grid_map, st));
+    return S1S2_OK;
+}
+
+}  // extern "C"

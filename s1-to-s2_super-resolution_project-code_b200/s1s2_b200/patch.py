@@ -1,0 +1,88 @@
+"""Patch.py's tiling on the device: window enumeration (host, integer-exact), tile extraction with per-patch
+normalisation and the overlap-blend stitch (CUDA gather kernels behind s1s2_tile_extract / s1s2_stitch).
+
+Reference: patch_iter Patch.py:80-84; slicing :201-203; build_mask :41-49; zscore_inplace :51-62 applied at
+:228-229; incidence / elevation scaling :231-232; invalid / non-finite -> 0 :236-239.  The stitch does not exist
+in the reference: uniform-weight average of all patches covering a pixel, patches
+visited in ascending index, uncovered pixels 0 with cover mask 0.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def patch_iter(H: int, W: int, ps: int, stride: int):
+    """Window origins (row, col) in the reference's order: rows outer, columns inner; remainder not covered."""
+    for r in range(0, H - ps + 1, stride):
+        for c in range(0, W - ps + 1, stride):
+            yield r, c
+
+
+def tile_origins(H: int, W: int, ps: int, stride: int) -> np.ndarray:
+    return np.array(list(patch_iter(H, W, ps, stride)), dtype=np.int32).reshape(-1, 2)
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous near-equal split of n units: rank r owns [lo, hi)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _dev_index(t: torch.Tensor) -> int:
+    if t.device.type != "cuda":
+        raise _lib.S1S2Error("patch kernels run on a CUDA device only (no CPU fallback)")
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def tile_extract(scene: torch.Tensor, origins, ps: int, vmask: torch.Tensor = None):
+    """scene f32[4,SH,SW] (cuda) -> (cond f32[N,4,ps,ps], mask u8[N,ps,ps], valid_ratio f32[N])."""
+    dev = scene.device
+    idx = _dev_index(scene)
+    scene = scene.to(torch.float32).contiguous()
+    if scene.ndim != 3 or scene.shape[0] != 4:
+        raise ValueError(f"scene must be f32[4,H,W], got {tuple(scene.shape)}")
+    org = torch.as_tensor(np.ascontiguousarray(origins, dtype=np.int32)).reshape(-1, 2)
+    N = org.shape[0]
+    SH, SW = scene.shape[1:]
+    if N and (int(org.min()) < 0 or int(org[:, 0].max()) + ps > SH or int(org[:, 1].max()) + ps > SW):
+        raise ValueError("window outside the scene")
+    org_d = org.to(dev)
+    cond = torch.empty((N, 4, ps, ps), device=dev, dtype=torch.float32)
+    mask = torch.empty((N, ps, ps), device=dev, dtype=torch.uint8)
+    ratio = torch.empty((N,), device=dev, dtype=torch.float32)
+    vm = None
+    if vmask is not None:
+        vm = vmask.to(device=dev, dtype=torch.uint8).contiguous()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(_lib.lib().s1s2_tile_extract(idx, scene.data_ptr(), vm.data_ptr() if vm is not None else None, SH, SW,
+                                            org_d.data_ptr(), N, ps, cond.data_ptr(), mask.data_ptr(), ratio.data_ptr(),
+                                            C.c_void_p(stream)))
+    return cond, mask, ratio
+
+
+def stitch(preds: torch.Tensor, origins, ps: int, stride: int, SH: int, SW: int):
+    """preds f32[N,C,ps,ps] (cuda) + origins on the stride grid -> (canvas f32[C,SH,SW], cover u8[SH,SW])."""
+    dev = preds.device
+    idx = _dev_index(preds)
+    preds = preds.to(torch.float32).contiguous()
+    org = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+    N, Cn = preds.shape[0], preds.shape[1]
+    if org.shape[0] != N:
+        raise ValueError("one origin per patch")
+    if N:
+        if (org % stride).any() or org.min() < 0 or org[:, 0].max() + ps > SH or org[:, 1].max() + ps > SW:
+            raise ValueError("origins must lie on the stride grid inside the scene")
+        key = org[:, 0].astype(np.int64) * (SW + 1) + org[:, 1]
+        if (np.diff(key) <= 0).any():
+            raise ValueError("origins must be strictly ascending in (row, col) order (Patch.py iteration order)")
+    org_d = torch.as_tensor(org).to(dev)
+    canvas = torch.empty((Cn, SH, SW), device=dev, dtype=torch.float32)
+    cover = torch.empty((SH, SW), device=dev, dtype=torch.uint8)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(_lib.lib().s1s2_stitch(idx, preds.data_ptr(), org_d.data_ptr(), N, Cn, ps, stride, SH, SW, canvas.data_ptr(),
+                                      cover.data_ptr(), C.c_void_p(stream)))
+    return canvas, cover
