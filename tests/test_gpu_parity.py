@@ -1,0 +1,294 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the ctypes mirror) against the CPU oracle.
+
+Tolerances:
+  * per-layer, isolated, fp16-rounded weights and inputs: max|err| <= 2^-9 * max|ref| (fp16 store rounding + order)
+  * model call vs fp32 oracle: rel-L2 <= 5e-3 and max|err| <= 2e-2 * max|ref| (fp16 operands, fp32 accumulate)
+  * scheduler update given the network output: bit-exact (fp32, same operation order, no FMA contraction)
+  * free-running v-DDIM image: PSNR(ours, oracle) >= 40 dB, |PSNR/SSIM vs target| within 0.1 dB / 0.002
+  * tiling indices, masks, stitch: bit-exact; z-score values <= 2e-6 abs
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as ometrics
+from oracle import patch as opatch
+from oracle import samplers as osamplers
+from oracle import schedule as osched
+from oracle import unet as ounet
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def env():
+    import s1s2_b200
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda:0")
+    sd = ounet.init_state_dict(8, 4, 96, seed=1234)
+    model = s1s2_b200.UNetSmallB200(8, 4, 96, max_batch=4).to(dev)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    _, alphas, abar = osched.make_schedule(1000)
+    return dict(dev=dev, sd=sd, model=model, oracle=ounet.OracleModel(sd), abar=abar, alphas=alphas)
+
+
+def _inputs(B, H, W, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    cond = torch.randn((B, 4, H, W), generator=g)
+    cond[:, 2] = torch.rand((B, H, W), generator=g) * 0.4 + 0.2
+    cond[:, 3] = (torch.randn((B, H, W), generator=g) * 0.3 + 0.3).abs()
+    x = torch.randn((B, 4, H, W), generator=g)
+    return x, cond
+
+
+# ------------------------------------------------------------------------------------------------ denoiser
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 64, 64), (1, 48, 80), (1, 256, 256)])
+def test_layers_isolated(env, B, H, W):
+    from layer_ref import check_layers
+    x, cond = _inputs(B, H, W, seed=B * 1000 + H)
+    t = torch.tensor([999, 20, 501][:B], dtype=torch.long)
+    y = env["model"](torch.cat([x, cond], 1).to(env["dev"]), t.to(env["dev"]))
+    torch.cuda.synchronize()
+    rows = check_layers(env["model"], env["sd"], y, B)
+    bad = [(n, e, m) for n, e, m, _ in rows if not e <= 2.0 ** -9 * m + 1e-6]
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 256, 256)])
+def test_model_call_vs_oracle(env, B, H, W):
+    x, cond = _inputs(B, H, W, seed=11)
+    t = torch.tensor([999, 20][:B], dtype=torch.long)
+    xin = torch.cat([x, cond], 1)
+    ref = env["oracle"](xin, t)
+    got = env["model"](xin.to(env["dev"]), t.to(env["dev"])).cpu()
+    rel = float((got - ref).norm() / ref.norm())
+    assert rel <= 5e-3, rel
+    assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+
+
+def test_batch_independent_and_deterministic(env):
+    B, H, W = 4, 64, 64
+    x, cond = _inputs(B, H, W, seed=5)
+    t = torch.tensor([999, 979, 20, 0], dtype=torch.long)
+    xin = torch.cat([x, cond], 1).to(env["dev"])
+    y1 = env["model"](xin, t.to(env["dev"])).clone()
+    y2 = env["model"](xin, t.to(env["dev"])).clone()
+    assert torch.equal(y1, y2)
+    for i in range(B):
+        yi = env["model"](xin[i:i + 1], t[i:i + 1].to(env["dev"]))
+        assert torch.equal(yi[0], y1[i]), i
+
+
+def test_drop_in_surface(env):
+    import s1s2_b200
+    m = env["model"]
+    assert m.outc.out_channels == 4
+    assert list(m.state_dict().keys()) == list(ounet.param_shapes(8, 4, 96).keys())
+    with pytest.raises(s1s2_b200.S1S2Error):
+        m(torch.zeros(1, 8, 32, 32, device="cuda")[:, :, :, :].cpu(), torch.zeros(1, dtype=torch.long))   # CPU tensor
+    bad = dict(env["sd"])
+    bad.pop("outc.bias")
+    with pytest.raises(RuntimeError):
+        s1s2_b200.UNetSmallB200(8, 4, 96).load_state_dict(bad, strict=True)
+    with pytest.raises(s1s2_b200.S1S2Error):
+        s1s2_b200.UNetSmallB200(8, 4, 64).to(env["dev"])(torch.zeros(1, 8, 32, 32, device="cuda"),
+                                                      torch.zeros(1, dtype=torch.long, device="cuda"))
+    with pytest.raises(s1s2_b200.S1S2Error):
+        m(torch.zeros(1, 8, 30, 32, device="cuda"), torch.zeros(1, dtype=torch.long, device="cuda"))     # H % 16
+
+
+# ------------------------------------------------------------------------------------------------ samplers
+def _ref_update(st, x_in, pred, z):
+    """The reference's elementwise scheduler code for one step record (fp32 torch, reference operation order)."""
+    from s1s2_b200 import _lib
+    c0, c1, c2, c3, c4 = (torch.tensor(v, dtype=torch.float32) for v in (st.c0, st.c1, st.c2, st.c3, st.c4))
+    if st.kind == _lib.STEP_EPS_DDIM:
+        x0, e = (x_in - c0 * pred) / c1, pred
+    elif st.kind in (_lib.STEP_V_DDIM, _lib.STEP_V_DDPM):
+        x0, e = c0 * x_in - c1 * pred, c1 * x_in + c0 * pred
+    else:
+        x0, e = None, pred
+    ddpm = st.kind in (_lib.STEP_EPS_DDPM, _lib.STEP_V_DDPM)
+    xn = c2 * (x_in - c3 * e) if ddpm else c2 * x0 + c3 * e
+    if st.flags & _lib.STEP_NOISE:
+        xn = xn + c4 * z
+    if st.flags & _lib.STEP_FINAL:
+        xn = torch.clamp(xn if ddpm else x0, 0.0, 1.0)
+    return xn
+
+
+def _teacher_forced(env, steps, cond, x_init, init_scale=1.0, step_noise=None):
+    from s1s2_b200 import _lib, samplers
+    dev = env["dev"]
+    out, taps = samplers.run_steps(env["model"], steps, cond.to(dev), x_init.to(dev), init_scale=init_scale,
+                                   step_noise=None if step_noise is None else step_noise.to(dev),
+                                   tap_pred=True, tap_x=True)
+    torch.cuda.synchronize()
+    B = cond.shape[0]
+    x_in = x_init * torch.tensor(init_scale, dtype=torch.float32)
+    worst = 0.0
+    for i, st in enumerate(steps):
+        ref = env["oracle"](torch.cat([x_in, cond], 1), torch.full((B,), st.t, dtype=torch.long))
+        got = taps["pred"][i].cpu()
+        rel = float((got - ref).norm() / ref.norm())
+        worst = max(worst, rel)
+        assert rel <= 5e-3, (i, st.t, rel)
+        assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max()), (i, st.t)
+        z = step_noise[st.noise_index] if st.flags & _lib.STEP_NOISE else None
+        want = _ref_update(st, x_in, got, z)
+        x_out = taps["x"][i].cpu()
+        assert torch.equal(x_out, want), (i, st.t, float((x_out - want).abs().max()))
+        x_in = x_out
+    assert torch.equal(out.cpu(), x_in)
+    return worst
+
+
+def test_eps_ddim_grid_a_teacher_forced(env):
+    from s1s2_b200 import schedule
+    x, cond = _inputs(2, 32, 32, seed=21)
+    _teacher_forced(env, schedule.steps_eps_grid_a(env["abar"], 999, 6), cond, x)
+    _teacher_forced(env, schedule.steps_eps_grid_a(env["abar"], 200, 5), cond, x)
+
+
+def test_v_ddim_grid_b_teacher_forced(env):
+    from s1s2_b200 import schedule
+    x, cond = _inputs(2, 32, 32, seed=22)
+    ab = env["abar"]
+    _teacher_forced(env, schedule.steps_grid_b(ab, schedule.grid_b(999, 6), "v"), cond, x,
+                    init_scale=float(torch.sqrt(1 - ab[999])))
+
+
+def test_stochastic_chains_teacher_forced(env):
+    from s1s2_b200 import schedule
+    x, cond = _inputs(2, 32, 32, seed=23)
+    ab = env["abar"]
+    g = torch.Generator().manual_seed(99)
+    zs = torch.randn((8, 2, 4, 32, 32), generator=g)
+    _teacher_forced(env, schedule.steps_grid_b(ab, schedule.grid_b(999, 5), "v", eta=0.05), cond, x,
+                    init_scale=float(torch.sqrt(1 - ab[999])), step_noise=zs)
+    b16 = osched.cosine_betas(16)
+    a16 = 1 - b16
+    ab16 = torch.cumprod(a16, 0)
+    for param in ("eps", "v"):
+        _teacher_forced(env, schedule.steps_ddpm(b16, a16, ab16, param, t_list=[15, 9, 3, 1, 0]), cond, x, step_noise=zs)
+
+
+def test_v_ddim_free_running_image_agreement(env):
+    from s1s2_b200 import samplers
+    B, H, W = 2, 32, 32
+    x, cond = _inputs(B, H, W, seed=31)
+    ab = env["abar"]
+    ref = osamplers.ddim_v_grid_b(env["oracle"], cond, ab, x, 10)
+    got = samplers.sample_ddim_v(env["model"], cond.to(env["dev"]), ab, 4, steps=10, eta=0.0, noise=x.to(env["dev"])).cpu()
+    assert ometrics.psnr(got, ref) >= 40.0
+    tgt = torch.rand((B, 4, H, W), generator=torch.Generator().manual_seed(3))
+    assert abs(ometrics.psnr(got, tgt) - ometrics.psnr(ref, tgt)) <= 0.1
+    assert abs(ometrics.ssim_simple(got, tgt) - ometrics.ssim_simple(ref, tgt)) <= 0.002
+
+
+def test_eps_recon_free_running_image_agreement(env):
+    from s1s2_b200 import samplers
+    x, cond = _inputs(1, 32, 32, seed=32)
+    ab = env["abar"]
+    x_gt = torch.rand((1, 4, 32, 32), generator=torch.Generator().manual_seed(4))
+    x_init = osamplers.noise_gt(x_gt, ab, 200, x)
+    ref = osamplers.ddim_eps_grid_a(env["oracle"], cond, ab, x_init, 200, 20)
+    mask = torch.ones((1, 32, 32))
+    mae, mse, got = samplers.ddim_multistep_eval(env["model"], x_gt.to(env["dev"]), cond.to(env["dev"]), ab,
+                                                 mask.to(env["dev"]), t_start=200, steps=20, noise=x.to(env["dev"]))
+    got = got.cpu()
+    assert ometrics.psnr(got, ref) >= 40.0
+    assert abs(ometrics.psnr(got, x_gt) - ometrics.psnr(ref, x_gt)) <= 0.1
+    assert abs(mae - ometrics.masked_mae(ref, x_gt)) <= 1e-3
+
+
+def test_sample_host_matches_device_entry(env):
+    from s1s2_b200 import samplers, schedule
+    x, cond = _inputs(2, 32, 32, seed=41)
+    steps = schedule.steps_grid_b(env["abar"], schedule.grid_b(999, 4), "v")
+    s = float(torch.sqrt(1 - env["abar"][999]))
+    a = samplers.run_steps(env["model"], steps, cond.to(env["dev"]), x.to(env["dev"]), init_scale=s).cpu()
+    b = samplers.run_steps_host(env["model"], steps, cond.pin_memory(), x.pin_memory(), init_scale=s, device=env["dev"])
+    assert torch.equal(a, b)
+
+
+def test_full_size_batch_properties(env):
+    """BASELINE-size property checks (256x256): clamp range, determinism, independence of patches in a batch."""
+    from s1s2_b200 import samplers, schedule
+    B = 4
+    x, cond = _inputs(B, 256, 256, seed=51)
+    ab = env["abar"]
+    steps = schedule.steps_grid_b(ab, schedule.grid_b(999, 3), "v")
+    s = float(torch.sqrt(1 - ab[999]))
+    y = samplers.run_steps(env["model"], steps, cond.to(env["dev"]), x.to(env["dev"]), init_scale=s).clone()
+    y2 = samplers.run_steps(env["model"], steps, cond.to(env["dev"]), x.to(env["dev"]), init_scale=s).clone()
+    assert torch.equal(y, y2)
+    assert float(y.min()) >= 0.0 and float(y.max()) <= 1.0 and torch.isfinite(y).all()
+    y1 = samplers.run_steps(env["model"], steps, cond[2:3].to(env["dev"]), x[2:3].to(env["dev"]), init_scale=s)
+    assert torch.equal(y1[0], y[2])
+
+
+# ------------------------------------------------------------------------------------------------ patch I/O
+def test_tile_extract_matches_golden(env):
+    from s1s2_b200 import patch
+    z = np.load(os.path.join(G, "patch.npz"))
+    ps, st = (int(v) for v in z["norm/ps_stride"])
+    scene = z["norm/scene"]
+    org = patch.tile_origins(scene.shape[1], scene.shape[2], ps, st)
+    assert np.array_equal(org, z["norm/origins"])
+    cond, mask, ratio = patch.tile_extract(torch.from_numpy(scene).to(env["dev"]), org, ps)
+    assert np.array_equal(mask.cpu().numpy(), z["norm/mask"])
+    assert np.abs(cond.cpu().numpy() - z["norm/cond"]).max() <= 2e-6
+    assert np.allclose(ratio.cpu().numpy(), z["norm/mask"].reshape(len(org), -1).mean(1), atol=1e-7)
+
+
+def test_tile_extract_edge_cases(env):
+    from s1s2_b200 import patch
+    rng = np.random.default_rng(3)
+    scene = rng.normal(-12, 4, (4, 70, 90)).astype(np.float32)
+    scene[:, :40, :40] = np.nan                     # one window fully invalid
+    scene[0, 38:, 57:] = 5.0                        # window (38,57): constant channel -> sigma < 1e-6 -> 1
+    scene[1, 45, 70] = np.inf
+    vm = opatch.valid_mask(scene)
+    org = opatch.tile_origins(70, 90, 32, 19)
+    cond, mask, _ = patch.tile_extract(torch.from_numpy(scene).to(env["dev"]), org, 32)
+    for i, (r, c) in enumerate(org):
+        X, M, _ = opatch.extract_patch(scene, vm, int(r), int(c), 32)
+        assert np.array_equal(mask[i].cpu().numpy(), M), i
+        assert np.abs(cond[i].cpu().numpy() - X).max() <= 2e-6, i
+    c0, m0, _ = patch.tile_extract(torch.from_numpy(scene).to(env["dev"]), np.zeros((0, 2), np.int32), 32)
+    assert c0.shape == (0, 4, 32, 32) and m0.shape == (0, 32, 32)
+
+
+@pytest.mark.parametrize("H,W,ps,st", [(40, 56, 16, 8), (70, 93, 32, 19), (64, 64, 64, 64)])
+def test_stitch_bitexact_vs_oracle(env, H, W, ps, st):
+    from s1s2_b200 import patch
+    rng = np.random.default_rng(H)
+    org = opatch.tile_origins(H, W, ps, st)
+    preds = rng.random((len(org), 4, ps, ps)).astype(np.float32)
+    keep = np.ones(len(org), bool)
+    if len(org) > 3:
+        keep[[1, len(org) // 2]] = False            # skipped patches are simply absent
+    ref, cov = opatch.stitch(preds[keep], org[keep], H, W)
+    canvas, cover = patch.stitch(torch.from_numpy(preds[keep]).to(env["dev"]), org[keep], ps, st, H, W)
+    assert np.array_equal(cover.cpu().numpy(), cov)
+    assert np.array_equal(canvas.cpu().numpy(), ref)
+
+
+def test_extract_sample_stitch_roundtrip(env):
+    """Size-independent property: identical overlaps blend to themselves (stitch o extract == identity on covered
+    pixels for the un-normalised channels)."""
+    from s1s2_b200 import patch
+    H, W, ps, st = 512, 768, 256, 64
+    g = torch.Generator().manual_seed(8)
+    truth = torch.rand((4, H, W), generator=g).to(env["dev"])
+    org = patch.tile_origins(H, W, ps, st)
+    tiles = torch.stack([truth[:, r:r + ps, c:c + ps] for r, c in org])
+    canvas, cover = patch.stitch(tiles, org, ps, st, H, W)
+    assert bool(cover.all())
+    assert float((canvas - truth).abs().max()) <= 1e-6

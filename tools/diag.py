@@ -1,0 +1,60 @@
+"""GPU bring-up diagnostic (run under gpurun): per-layer isolated errors, then a quick timing.
+usage: python tools/diag.py layers B H W | time B steps"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "s1-to-s2_super-resolution_project-code_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+from oracle import schedule as osched, unet as ounet  # noqa: E402
+import s1s2_b200  # noqa: E402
+from s1s2_b200 import samplers, schedule  # noqa: E402
+
+
+def make(max_batch):
+    sd = ounet.init_state_dict(8, 4, 96, seed=1234)
+    m = s1s2_b200.UNetSmallB200(8, 4, 96, max_batch=max_batch).to("cuda")
+    m.load_state_dict(sd)
+    return sd, m.eval()
+
+
+def main():
+    mode = sys.argv[1]
+    if mode == "layers":
+        from layer_ref import check_layers
+        B, H, W = (int(v) for v in sys.argv[2:5])
+        sd, m = make(B)
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn((B, 8, H, W), generator=g)
+        t = torch.tensor([999, 20, 501, 0][:B], dtype=torch.long)
+        y = m(x.cuda(), t.cuda())
+        torch.cuda.synchronize()
+        print(f"forward ok B={B} {H}x{W}; isolated per-layer errors:", flush=True)
+        check_layers(m, sd, y, B, verbose=True)
+        ref = ounet.OracleModel(sd)(x, t)
+        print("end-to-end rel-L2 vs fp32 oracle:", float((y.cpu() - ref).norm() / ref.norm()), flush=True)
+    elif mode == "time":
+        B, nsteps = int(sys.argv[2]), int(sys.argv[3])
+        sd, m = make(B)
+        _, _, ab = osched.make_schedule(1000)
+        steps = schedule.steps_grid_b(ab, schedule.grid_b(999, nsteps), "v")
+        cond = torch.randn((B, 4, 256, 256), device="cuda")
+        x = torch.randn((B, 4, 256, 256), device="cuda")
+        samplers.run_steps(m, steps[:2], cond, x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        samplers.run_steps(m, steps, cond, x)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        fl = B * len(steps) * 301.851e9
+        print(f"B={B} steps={len(steps)}: {ms:.1f} ms, {ms/len(steps):.2f} ms/step, {fl/ms/1e9:.1f} TFLOP/s, "
+              f"{B/(ms/1e3)*len(steps)/50:.2f} DDIM-50-equivalent patches/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
