@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""DDIM-50 patches/sec of the S1->S2 sampling path on N B200s (one process per GPU), next to the CPU oracle.
+
+A "step" is one complete DDIM-50 sampling (50 fused model calls + scheduler updates) of one batch of synthetic
+256x256 patches per GPU.  Workloads (BASELINE.json configs):
+  v64   v-prediction UNet, grid B (0..999, 50 entries), eta=0, batch 64 per GPU     [default; north-star target]
+  eps16 eps-prediction UNet, grid A (999 -> 0, 50 calls), batch 16 per GPU
+Patches are independent units: N GPUs = N x batch patches per step, no data-path collective ("weak" scaling).
+
+  value     patches/s with inputs resident in HBM (CUDA events, barrier + synchronize on both sides, max over ranks)
+  e2e       the same through the host-buffer entry s1s2_sample_host (pinned host cond + noise in, image out)
+  roofline  tensor-pipe roofline of the conv kernel family (every launch in the timed region is one instantiation of
+            conv_umma_kernel): algorithmic FLOPs (301 851 475 968 per patch per model call)
+            / device time, against MEASURED_PEAKS.json's sustained bf16 figure; `layers` lists every launch of one
+            model call timed with a CUDA event pair on the launching stream.
+  cpu_baseline  oracle/ (a port of the reference's PyTorch sampler) timed on this box's host cores, bounded sample.
+
+`--impl reference` times only the CPU oracle port (the reference is Python/PyTorch and does not travel to the GPU
+box; oracle/ is its restatement, pinned against vectors the real reference produced: tests/golden/).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "s1-to-s2_super-resolution_project-code_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+FLOP_PER_CALL = 301_851_475_968          # per 256x256 patch per model call (measured on the reference)
+H = W = 256
+N_CALLS = 50
+
+
+def layer_flops():
+    """2*M*N*K of every launch of one model call (execution order), per patch; sums to FLOP_PER_CALL."""
+    b = 96
+    rows = [("inc.0", 256, b, 9 * 9)]
+    c, s = b, 256
+    for lvl in ("down1", "down2", "down3"):
+        rows += [(f"{lvl}.0.0", s, 2 * c, 9 * c), (f"{lvl}.0.2", s, 2 * c, 9 * 2 * c)]
+        c, s = 2 * c, s // 2
+    for up, blk in (("up3", "conv3"), ("up2", "conv2"), ("up1", "conv1")):
+        rows += [(up, s, 4 * (c // 2), c)]
+        s *= 2
+        rows += [(f"{blk}.0", s, c // 2, 9 * c), (f"{blk}.2", s, c // 2, 9 * (c // 2))]
+        c //= 2
+    out = [(n, 2 * side * side * N * K) for n, side, N, K in rows]
+    out[-1] = (out[-1][0], out[-1][1] + 2 * 256 * 256 * 4 * 96)      # outc rides in conv1.2's epilogue
+    assert sum(f for _, f in out) == FLOP_PER_CALL
+    return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops_sustained"]), float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synthetic_batch(B, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    cond = torch.randn((B, 4, H, W), generator=g)
+    cond[:, 2] = torch.rand((B, H, W), generator=g) * 0.4 + 0.2
+    cond[:, 3] = (torch.randn((B, H, W), generator=g) * 0.3 + 0.3).abs()
+    noise = torch.randn((B, 4, H, W), generator=g)
+    return cond, noise
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c, w in zip(sm, power) if w >= 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+def make_steps(workload, abar):
+    from s1s2_b200 import schedule
+    import torch
+    if workload == "v64":
+        steps = schedule.steps_grid_b(abar, schedule.grid_b(999, 50), "v")
+        return steps, float(torch.sqrt(1 - abar[999]))
+    steps = schedule.steps_eps_grid_a(abar, 999, 50)
+    return steps, 1.0
+
+
+def cpu_oracle_sample(workload, n_calls, threads):
+    """Times `n_calls` model calls + scheduler updates of the DDIM-50 chain of ONE patch in the CPU oracle; returns
+    (seconds, patches/s extrapolated to the 50-call chain)."""
+    import torch
+    from oracle import samplers as osamplers, schedule as osched, unet as ounet
+    torch.set_num_threads(threads)
+    sd = ounet.init_state_dict(8, 4, 96, seed=1234 if workload == "eps16" else 1235)
+    model = ounet.OracleModel(sd)
+    _, _, abar = osched.make_schedule(1000)
+    cond, noise = synthetic_batch(1, 2024)
+    calls = {"n": 0}
+
+    class Stop(Exception):
+        pass
+
+    def counted(x, t):
+        if calls["n"] >= n_calls:
+            raise Stop()
+        calls["n"] += 1
+        return model(x, t)
+    counted.outc = model.outc
+    t0 = time.perf_counter()
+    try:
+        if workload == "v64":
+            osamplers.ddim_v_grid_b(counted, cond, abar, noise, 50)
+        else:
+            osamplers.ddim_eps_grid_a(counted, cond, abar, noise, 999, 50)
+    except Stop:
+        pass
+    dt = time.perf_counter() - t0
+    return dt, 1.0 / (dt * N_CALLS / calls["n"])
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_calls = 4
+    cpu_oracle_sample(args.workload, 1, threads)                       # page in torch / oneDNN
+    for _ in range(args.warmup):
+        cpu_oracle_sample(args.workload, 1, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_sample(args.workload, n_calls, threads)
+    dt = time.perf_counter() - t0
+    pps = args.steps / (dt * N_CALLS / n_calls)
+    sample = (f"each step = {n_calls} of the 50 model calls (+ scheduler updates) of one 256x256 patch, oracle/ fp32 "
+              f"PyTorch CPU, {threads} threads; patches/s extrapolated x{N_CALLS // n_calls}")
+    line = {"impl": "reference", "metric": "DDIM-50 patches/sec", "value": pps, "unit": "patches/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * N_CALLS / n_calls,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_block(args, world),
+            "cpu_baseline": {"value": pps, "unit": "patches/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": pps, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_block(args, world):
+    B = args.batch
+    return {"workload": ("DDIM_Multi-step_v_Prediction: v-prediction UNetSmall(8,4,96), grid B 0..999 (50 calls), eta=0"
+                         if args.workload == "v64" else
+                         "DDIM_Multi-step / Evaluation_Pure_Generation: eps-prediction UNetSmall(8,4,96), grid A 999->0 (50 calls)"),
+            "patch": "4x256x256 cond + 4x256x256 noise (Patch.py shape)", "batch_per_gpu": B, "global_batch": B * world,
+            "ddim_steps": 50, "weights": "random init (Models/*.pth absent from the reference tree)",
+            "parallelism": f"patch-sharded x{world}, no data-path collective",
+            "l2": "working set per step (activation arena ~123 MB/patch) exceeds the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="v64", choices=["v64", "eps16"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-layers", action="store_true")
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 64 if args.workload == "v64" else 16
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torch.distributed.run, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000)] + sys.argv
+        sys.exit(subprocess.call(cmd))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product path has no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+
+    import s1s2_b200
+    from s1s2_b200 import samplers, schedule
+    from oracle import unet as ounet               # weights only: the synthetic checkpoint both sides load
+
+    B = args.batch
+    sd = ounet.init_state_dict(8, 4, 96, seed=1234 if args.workload == "eps16" else 1235)
+    model = s1s2_b200.UNetSmallB200(8, 4, 96, max_batch=B).to(dev)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    _, _, abar = schedule.derive(schedule.cosine_beta_schedule(1000))
+    steps, init_scale = make_steps(args.workload, abar)
+    assert len(steps) == N_CALLS
+    cond_h, noise_h = synthetic_batch(B, 2024 + rank)
+    cond_h, noise_h = cond_h.pin_memory(), noise_h.pin_memory()
+    cond_d, noise_d = cond_h.to(dev), noise_h.to(dev)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- device-resident arm
+    for _ in range(args.warmup):
+        out = samplers.run_steps(model, steps, cond_d, noise_d, init_scale=init_scale)
+    sync()
+    clocks = ClockSampler(local)
+    l0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = samplers.run_steps(model, steps, cond_d, noise_d, init_scale=init_scale)
+    e1.record()
+    sync()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = model.launch_count() - l0
+    clk = clocks.stop()
+    assert bool(torch.isfinite(out).all())
+    patches = B * world * args.steps
+    value = patches / (ms / 1e3)
+
+    # ---------------------------------------------------------------- end-to-end arm (host buffers)
+    samplers.run_steps_host(model, steps, cond_h, noise_h, init_scale=init_scale, device=dev)
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        res = samplers.run_steps_host(model, steps, cond_h, noise_h, init_scale=init_scale, device=dev)
+    e1.record()
+    sync()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    img_bytes = B * 4 * H * W * 4
+    e2e = {"value": patches / (ms_e2e / 1e3), "unit": "patches/s", "h2d_bytes_per_step": 2 * img_bytes * world,
+           "d2h_bytes_per_step": img_bytes * world, "entry": "s1s2_sample_host (pinned host cond + noise -> host image)"}
+    assert bool(torch.equal(res, out.cpu())), "host-buffer entry disagrees with the device-resident entry"
+
+    # ---------------------------------------------------------------- roofline of the conv kernel family
+    peak_tf, _, peak_src = peaks()
+    flop_step = FLOP_PER_CALL * N_CALLS * B                      # per GPU per step
+    achieved = flop_step * args.steps / (ms / 1e3) / 1e12       # TFLOP/s per GPU over the timed region
+    roof = {"bound": "tensor", "kernel": "conv_umma_kernel<BLOCK_N,KBOX,BOXES,STAGES,MODE> (all 16 launches of a model "
+            "call; timed region = 50 model calls x steps, nothing else launches)", "achieved": achieved, "peak": peak_tf,
+            "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src, "traffic": None,
+            "flop_per_launch_avg": FLOP_PER_CALL * B / 16}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        roof["traffic"] = json.load(open(tp))
+    if not args.no_layers and rank == 0:
+        lt = model.profile_layers(dev, H, W, B, reps=3)
+        fl = dict(layer_flops())
+        roof["layers"] = [{"layer": n, "ms": round(t, 4), "tflops": round(fl[n] * B / (t / 1e3) / 1e12, 1)} for n, t in lt]
+        top = max(roof["layers"], key=lambda r: r["ms"])
+        roof["dominant_launch"] = top
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cpu_oracle_sample(args.workload, 1, threads)
+        n_calls = 10
+        dt, pps = cpu_oracle_sample(args.workload, n_calls, threads)
+        cpu = {"value": pps, "unit": "patches/s", "cores": threads, "kind": "port",
+               "sample": f"{n_calls} of the 50 model calls of one patch ({dt:.1f} s), oracle/ fp32 PyTorch CPU, extrapolated x5"}
+
+    if rank == 0:
+        line = {"metric": "DDIM-50 patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (TMEM) and f32 scheduler state",
+                "data": "synthetic", "config": config_block(args, world), "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

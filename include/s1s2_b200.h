@@ -115,6 +115,14 @@ int s1s2_stitch(int device, const float* preds, const int32_t* origins, int N, i
 int s1s2_debug_activation(s1s2_handle* h, const char* name, float* out_nchw, int B, int* C, int* H, int* W,
                           void* stream);
 
+/* Measurement aid for bench.py's roofline block: runs the denoiser `reps` times at batch B on whatever the arena
+ * holds, with a CUDA event pair around every launch on `stream`, and returns the mean duration of each launch in
+ * milliseconds (ms_out[i], i < n_out; launch order = the network's execution order, see s1s2_layer_name).  Host-
+ * synchronous.  Returns the number of launches per model call through *n_layers. */
+int s1s2_profile_layers(s1s2_handle* h, int B, int reps, float* ms_out, int n_out, int* n_layers, void* stream);
+/* state_dict prefix of the i-th launch of a model call ("inc.0", "down1.0.0", ... "conv1.2"), NULL past the end. */
+const char* s1s2_layer_name(const s1s2_handle* h, int i);
+
 /* Number of kernels this library launched on behalf of `h` since creation (bench.py's gpu_launches). */
 int64_t s1s2_launch_count(const s1s2_handle* h);
 

@@ -702,6 +702,59 @@ int s1s2_debug_activation(s1s2_handle* h, const char* name, float* out_nchw, int
     return S1S2_ERR_INVALID;
 }
 
+const char* s1s2_layer_name(const s1s2_handle* h, int i) {
+    if (h == nullptr || i < 0 || i >= static_cast<int>(h->layers.size())) return nullptr;
+    return h->layers[i].name;
+}
+
+int s1s2_profile_layers(s1s2_handle* h, int B, int reps, float* ms_out, int n_out, int* n_layers, void* stream) {
+    int rc = check_batch(h, B);
+    if (rc != S1S2_OK) return rc;
+    std::string* err = &h->err;
+    const int nl = static_cast<int>(h->layers.size());
+    if (n_layers != nullptr) *n_layers = nl;
+    if (ms_out == nullptr) return S1S2_OK;
+    if (reps < 1 || n_out < nl) {
+        set_err(err, "s1s2_profile_layers: reps %d, n_out %d (need >= %d)", reps, n_out, nl);
+        return S1S2_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    std::vector<cudaEvent_t> ev(static_cast<size_t>(reps) * (nl + 1));
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    HeadParams io;
+    memset(&io, 0, sizeof(io));
+    io.step.kind = STEP_NONE;
+    for (int r = 0; r < reps; ++r) {
+        for (int i = 0; i < nl; ++i) {
+            Layer& L = h->layers[i];
+            if (L.kid == K_HEAD) {
+                HeadParams& hp = L.p.head;
+                memcpy(hp.w, h->head_w, sizeof(hp.w));
+                memcpy(hp.b, h->head_b, sizeof(hp.b));
+                hp.x_t = nullptr; hp.pred_out = nullptr; hp.noise = nullptr; hp.xin16 = nullptr;
+                hp.step = io.step;
+            }
+            CK(cudaEventRecord(ev[r * (nl + 1) + i], st));
+            rc = launch_layer(h, L, B, st, err);
+            if (rc != S1S2_OK) return rc;
+        }
+        CK(cudaEventRecord(ev[r * (nl + 1) + nl], st));
+    }
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < nl; ++i) {
+        double acc = 0.0;
+        for (int r = 0; r < reps; ++r) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ev[r * (nl + 1) + i], ev[r * (nl + 1) + i + 1]));
+            acc += ms;
+        }
+        ms_out[i] = static_cast<float>(acc / reps);
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return S1S2_OK;
+}
+
 int s1s2_tile_extract(int device, const float* scene, const uint8_t* vmask, int SH, int SW, const int32_t* origins, int N,
                       int ps, float* cond, uint8_t* mask, float* valid_ratio, void* stream) {
     std::string* err = &g_error;

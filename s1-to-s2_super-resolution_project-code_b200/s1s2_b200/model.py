@@ -107,6 +107,17 @@ class UNetSmallB200(nn.Module):
     def launch_count(self) -> int:
         return sum(int(_lib.lib().s1s2_launch_count(e.h)) for e in self._engines.values())
 
+    def profile_layers(self, device, H: int, W: int, batch: int, reps: int = 3):
+        """[(state_dict prefix, mean ms per launch)] of one model call at this geometry (s1s2_profile_layers)."""
+        eng = self.engine(torch.device(device), H, W, batch)
+        L = _lib.lib()
+        n = C.c_int()
+        _lib.check(L.s1s2_profile_layers(eng.h, batch, reps, None, 0, C.byref(n), None), eng.h)
+        ms = (C.c_float * n.value)()
+        stream = torch.cuda.current_stream(torch.device(device)).cuda_stream
+        _lib.check(L.s1s2_profile_layers(eng.h, batch, reps, ms, n.value, C.byref(n), C.c_void_p(stream)), eng.h)
+        return [(L.s1s2_layer_name(eng.h, i).decode(), float(ms[i])) for i in range(n.value)]
+
     # ------------------------------------------------------------------ the reference's call
     @torch.no_grad()
     def forward(self, xt_and_cond: torch.Tensor, t_idx: torch.Tensor) -> torch.Tensor:

@@ -73,7 +73,11 @@ def run_steps_host(model: UNetSmallB200, steps, cond_host, x_init_host, init_sca
     assert cond_host.device.type == "cpu" and x_init_host.device.type == "cpu"
     cond_host = cond_host.to(torch.float32).contiguous()
     x_init_host = x_init_host.to(torch.float32).contiguous()
-    out = torch.empty(x_init_host.shape, dtype=torch.float32, pin_memory=True)
+    key = ("host_out", tuple(x_init_host.shape))
+    cache = model.__dict__.setdefault("_host_buffers", {})
+    out = cache.get(key)
+    if out is None:          # pinned result buffer, reused across calls (the caller copies out of it if it keeps it)
+        out = cache[key] = torch.empty(x_init_host.shape, dtype=torch.float32, pin_memory=True)
     n = len(steps)
     arr = (_lib.Step * n)(*steps)
     stream = torch.cuda.current_stream(dev).cuda_stream
