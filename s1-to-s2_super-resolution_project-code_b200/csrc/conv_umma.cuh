@@ -1,5 +1,5 @@
-// Implicit-GEMM convolution for the UNetSmall denoiser on sm_100a: TMA-fed, tcgen05.mma with the accumulator in
-// TMEM, warp-specialised and persistent (one CTA per SM).
+// Implicit-GEMM convolution for the UNetSmall denoiser on sm_100a: TMA-fed, tcgen05.mma.cta_group::2 with the
+// accumulator in TMEM, warp-specialised and persistent (one CTA per SM, CTAs paired into clusters of 2).
 //
 //   D[pixel, cout] = sum_{tap, cin} X[pixel shifted by tap, cin] * Wt[cout, tap, cin]
 //
@@ -13,9 +13,19 @@
 // by the TMA unit, which is exactly the conv's zero padding.  Weights are [cout][tap][cin] fp16 (K-major), one 2-D
 // TMA box per chunk.  Both operands land in the canonical K-major swizzled layout UMMA reads.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 =
-// epilogue (TMEM lane quadrant = warp_idx % 4).  Two TMEM accumulators so the epilogue of tile i overlaps the MMAs
-// of tile i+1.
+// CTA pair: the two CTAs of a cluster work on two consecutive M tiles and the same N tile.  Each CTA loads its own
+// 128 activation rows and HALF of the weight rows; one thread of the leader CTA issues M=256 MMAs that read both
+// CTAs' shared memory and write both CTAs' TMEM.  Halving the weight traffic per SM is what lifts the kernel off
+// the shared-memory bandwidth bound the single-CTA version sat on (profiles/r1a_*: 62-66 % tensor-pipe active).
+//
+// Warp roles (256 threads per CTA): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM
+// allocator, warps 4..7 = epilogue (TMEM lane quadrant = warp_idx % 4).  Two TMEM accumulators so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
+//
+// Dynamic range: activations are fp16, the reference is fp32.  Every model call carries a per-patch power-of-two
+// scale s = 2^k derived from max|x_t| (k = 0 while max|x_t| < 16): the first layer stores relu(.)/s, every later
+// layer adds bias/s, the head multiplies its output by s.  ReLU, max-pool and the convolutions are positively
+// homogeneous, so this is the same network; with k = 0 it is bit-identical to the unscaled arithmetic.
 #pragma once
 #include "ptx_sm100.cuh"
 
@@ -25,6 +35,9 @@ enum : int { MODE_STORE = 0, MODE_POOL = 1, MODE_CONVT = 2, MODE_HEAD = 3 };
 
 enum : int { STEP_NONE = 0, STEP_EPS_DDIM = 1, STEP_V_DDIM = 2, STEP_EPS_DDPM = 3, STEP_V_DDPM = 4 };
 enum : int { STEP_FLAG_FINAL = 1, STEP_FLAG_NOISE = 2 };
+enum : int { LAYER_FLAG_FIRST = 1 };   // first layer: apply the range scale in the epilogue (inputs are unscaled)
+
+constexpr float kXSplit = 4096.f;      // x_t travels as an fp16 pair: x = kXSplit * hi + lo
 
 // One scheduler update; travels by value in the kernel parameters, so a sampling loop is enqueued (or captured in
 // a CUDA graph) without device-side bookkeeping or host round trips.
@@ -49,6 +62,7 @@ struct HeadParams {
     float* pred_out;              // f32 NCHW eps / v (nullable)
     const float* noise;           // f32 NCHW per-step z (nullable)
     __half* xin16;                // next call's input planes, NHWC16 fp16 (nullable)
+    uint32_t* amax_out;           // [B] float bits of max|x_{next}| per patch (nullable)
     StepCoef step;                // by value: kind == STEP_NONE for a plain forward
 };
 
@@ -56,6 +70,7 @@ struct ConvParams {
     CUtensorMap tmap_a;
     CUtensorMap tmap_b;
     const float* bias;            // [num_n_tiles * BLOCK_N]
+    const uint32_t* amax_in;      // [B] float bits of max|x_t| per patch for this call (nullptr: scale 1)
     __half* out;                  // NHWC fp16 destination (channel offset already applied)
     int out_cpitch;               // elements between consecutive destination pixels
     int H, W, B;                  // input image size, live batch
@@ -65,13 +80,14 @@ struct ConvParams {
     int taps_w;                   // 3 -> 3x3 pad 1 ; 1 -> 1x1 / transposed-conv GEMM
     int chunks;                   // K chunks of KBOX channels per tap
     int cout;                     // real channels per output pixel (CONVT: per tap)
+    int flags;                    // LAYER_FLAG_*
     HeadParams head;              // MODE_HEAD only
 };
 
 template <int BLOCK_N, int KBOX, int BOXES, int STAGES>
 struct ConvSmem {
     static constexpr int kABox = 128 * KBOX * 2;
-    static constexpr int kBBox = BLOCK_N * KBOX * 2;
+    static constexpr int kBBox = (BLOCK_N / 2) * KBOX * 2;      // this CTA's half of the weight rows
     static constexpr int kStage = BOXES * (kABox + kBBox);
     static constexpr int kBias = 1536 * 4;
     static constexpr int kBytes = 1024 /*align slack*/ + STAGES * kStage + kBias + 256 /*barriers*/;
@@ -87,30 +103,48 @@ __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
     __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
 }
+// x = kXSplit * hi + lo with hi, lo fp16: ~22 significant bits and a range of 65504 * 4096.
+__device__ __forceinline__ void split_x(float x, float& hi, float& lo) {
+    hi = __half2float(__float2half_rn(fminf(fmaxf(x * (1.f / kXSplit), -65504.f), 65504.f)));
+    lo = x - kXSplit * hi;
+}
+// Range scale of a patch from the float bits of max|x_t|: exponent k = max(0, floor(log2(amax)) - 3), i.e.
+// amax / 2^k < 16.  Returns 2^-k (and 2^k through `s`).
+__device__ __forceinline__ float range_scale(uint32_t amax_bits, float& s) {
+    int k = static_cast<int>((amax_bits >> 23) & 0xFFu) - 127 - 3;
+    k = k < 0 ? 0 : (k > 100 ? 100 : k);
+    s = __uint_as_float(static_cast<uint32_t>(127 + k) << 23);
+    return __uint_as_float(static_cast<uint32_t>(127 - k) << 23);
+}
 
 template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE>
-__global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv_umma_kernel(const __grid_constant__ ConvParams p) {
     using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES>;
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
     static_assert(KBOX == 16 || KBOX == 32 || KBOX == 64, "KBOX");
     constexpr int kRowBytes = KBOX * 2;
     constexpr int kAccStride = 256;            // TMEM columns between the two accumulators
-    constexpr uint32_t kIdesc = umma_idesc_f16(128, BLOCK_N);
+    constexpr uint32_t kIdesc = umma_idesc_f16(256, BLOCK_N);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
     float* sbias = reinterpret_cast<float*>(smem + STAGES * L::kStage);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage + L::kBias);
-    uint64_t* full_bar = bars;                    // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
-    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
-    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
+    uint64_t* full_bar = bars;                    // [STAGES]   (leader's copy is the live one)
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]   (one per CTA, signalled by multicast commits)
+    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]        (one per CTA, multicast commits)
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]        (leader's copy is the live one)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int m_pairs = (p.num_m_tiles + 1) >> 1;
+    const int num_tiles = m_pairs * p.num_n_tiles;          // pair tiles: 2 M tiles x 1 N tile
     const int k_iters = (p.taps_w * p.taps_w * p.chunks) / BOXES;
     const int pad = p.taps_w >> 1;
 
@@ -120,43 +154,46 @@ __global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&full_bar[s], 1);         // leader's producer: arrive.expect_tx for both CTAs' bytes
+            mbar_init(&empty_bar[s], 1);        // one multicast commit
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 4);       // one arrive per epilogue warp
+            mbar_init(&tfull_bar[a], 1);        // one multicast commit
+            mbar_init(&tempty_bar[a], 8);       // one arrive per epilogue warp of both CTAs
         }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
     {   // bias for every N tile of this layer, staged once
         const int nb = p.num_n_tiles * BLOCK_N;
         for (int i = threadIdx.x; i < nb; i += blockDim.x) sbias[i] = p.bias[i];
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                         // peer's barriers are initialised before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================================================================= TMA producer
+        // ================================================================= TMA producer (both CTAs)
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int n_tile = tile % p.num_n_tiles;
-                const int m_tile = tile / p.num_n_tiles;
+                const int m_tile = 2 * (tile / p.num_n_tiles) + static_cast<int>(rank);
                 const int tx = m_tile % p.tiles_x;
                 const int ty = (m_tile / p.tiles_x) % p.tiles_y;
                 const int tn = m_tile / (p.tiles_x * p.tiles_y);
                 const int x0 = tx << p.tw_log2;
                 const int y0 = ty << p.th_log2;
-                const int n0 = tn << (7 - p.tw_log2 - p.th_log2);
+                const int n0 = tn << (7 - p.tw_log2 - p.th_log2);    // past the batch for a phantom tile: zero fill
+                const int b_row0 = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
                 int box = 0;
                 for (int it = 0; it < k_iters; ++it) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    mbar_expect_tx(&full_bar[s], L::kStage);
+                    const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[s]), 0);
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * L::kStage);
                     uint8_t* a_dst = stage_base + s * L::kStage;
                     uint8_t* b_dst = a_dst + BOXES * L::kABox;
 #pragma unroll
@@ -165,22 +202,22 @@ __global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant
                         const int chunk = box - tap * p.chunks;
                         const int ky = tap / p.taps_w;
                         const int kx = tap - ky * p.taps_w;
-                        tma_load_4d(a_dst + b * L::kABox, &p.tmap_a, &full_bar[s], chunk * KBOX, x0 + kx - pad,
-                                    y0 + ky - pad, n0);
-                        tma_load_2d(b_dst + b * L::kBBox, &p.tmap_b, &full_bar[s], box * KBOX, n_tile * BLOCK_N);
+                        tma_load_4d_pair(a_dst + b * L::kABox, &p.tmap_a, full_leader, chunk * KBOX, x0 + kx - pad,
+                                         y0 + ky - pad, n0);
+                        tma_load_2d_pair(b_dst + b * L::kBBox, &p.tmap_b, full_leader, box * KBOX, b_row0);
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================================================================= MMA issuer
-        if (lane == 0) {
+        // ================================================================= MMA issuer (leader CTA, one thread)
+        if (rank == 0 && lane == 0) {
             int s = 0;
             uint32_t ph = 0;
             int acc = 0;
             uint32_t acc_ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kAccStride;
@@ -196,11 +233,11 @@ __global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant
 #pragma unroll
                         for (int k = 0; k < KBOX / 16; ++k) {
                             // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
-                            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (it | b | k) != 0 ? 1u : 0u);
+                            umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (it | b | k) != 0 ? 1u : 0u);
                         }
                     }
-                    umma_commit(&empty_bar[s]);                 // smem slot reusable once these MMAs retire
-                    if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+                    umma_commit_pair(&empty_bar[s]);            // both CTAs' slots reusable once these MMAs retire
+                    if (it == k_iters - 1) umma_commit_pair(&tfull_bar[acc]);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 acc ^= 1;
@@ -217,9 +254,9 @@ __global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant
         const int ln = m >> (p.tw_log2 + p.th_log2);
         int acc = 0;
         uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int n_tile = tile % p.num_n_tiles;
-            const int m_tile = tile / p.num_n_tiles;
+            const int m_tile = 2 * (tile / p.num_n_tiles) + static_cast<int>(rank);
             const int tx = m_tile % p.tiles_x;
             const int ty = (m_tile / p.tiles_x) % p.tiles_y;
             const int tn = m_tile / (p.tiles_x * p.tiles_y);
@@ -227,17 +264,20 @@ __global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant
             const int y = (ty << p.th_log2) + ly;
             const int n = (tn << (7 - p.tw_log2 - p.th_log2)) + ln;
             const bool live = (n < p.B) && (y < p.H) && (x < p.W);
+            float s_up = 1.f, s_dn = 1.f;
+            if (live && p.amax_in != nullptr) s_dn = range_scale(__ldg(p.amax_in + n), s_up);
 
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
             const float* bias_t = sbias + n_tile * BLOCK_N;
+            const uint32_t tempty_leader = mapa_shared(smem_u32(&tempty_bar[acc]), 0);
 
             if constexpr (MODE == MODE_HEAD) {
                 static_assert(MODE != MODE_HEAD || BLOCK_N == kHeadIn, "head wants all channels of a pixel");
                 float o[kHeadOut];
 #pragma unroll
-                for (int k = 0; k < kHeadOut; ++k) o[k] = p.head.b[k];
+                for (int k = 0; k < kHeadOut; ++k) o[k] = p.head.b[k] * s_dn;
 #pragma unroll
                 for (int c = 0; c < BLOCK_N / 32; ++c) {
                     uint32_t r[32];
@@ -245,24 +285,25 @@ __global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float h = fmaxf(__uint_as_float(r[j]) + bias_t[c * 32 + j], 0.f);
+                        const float h = fmaxf(fmaf(bias_t[c * 32 + j], s_dn, __uint_as_float(r[j])), 0.f);
 #pragma unroll
                         for (int k = 0; k < kHeadOut; ++k) o[k] = fmaf(h, p.head.w[k * kHeadIn + c * 32 + j], o[k]);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // accumulator drained: MMAs of tile+2 may start
+                if (lane == 0) mbar_arrive_cluster(tempty_leader);  // accumulator drained: MMAs of tile+2 may start
 
+                const StepCoef& sc = p.head.step;
+                float amax = 0.f;
                 if (live) {
-                    const StepCoef& sc = p.head.step;
                     const size_t plane = static_cast<size_t>(p.H) * p.W;
                     const size_t pix = static_cast<size_t>(y) * p.W + x;
                     float res[kHeadOut];
 #pragma unroll
                     for (int k = 0; k < kHeadOut; ++k) {
                         const size_t idx = (static_cast<size_t>(n) * kHeadOut + k) * plane + pix;
-                        const float pr = o[k];
+                        const float pr = o[k] * s_up;
                         if (p.head.pred_out != nullptr) p.head.pred_out[idx] = pr;
                         res[k] = pr;
                         if (sc.kind != STEP_NONE) {
@@ -281,15 +322,36 @@ __global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant
                             if (sc.flags & STEP_FLAG_FINAL) xn = fminf(fmaxf(ddpm ? xn : x0, 0.f), 1.f);
                             p.head.x_t[idx] = xn;
                             res[k] = xn;
+                            amax = fmaxf(amax, fabsf(xn));
                         }
                     }
                     if (sc.kind != STEP_NONE && p.head.xin16 != nullptr) {
+                        float hi[kHeadOut], lo[kHeadOut];
+#pragma unroll
+                        for (int k = 0; k < kHeadOut; ++k) split_x(res[k], hi[k], lo[k]);
+                        __half* rec = p.head.xin16 + ((static_cast<size_t>(n) * p.H + y) * p.W + x) * 16;
                         uint4 v;
-                        v.x = pack_half2_sat(res[0], res[1]);
-                        v.y = pack_half2_sat(res[2], res[3]);
+                        v.x = pack_half2_sat(lo[0], lo[1]);
+                        v.y = pack_half2_sat(lo[2], lo[3]);
                         v.z = pack_half2_sat(sc.t_next, sc.t_next);
                         v.w = 0u;
-                        *reinterpret_cast<uint4*>(p.head.xin16 + ((static_cast<size_t>(n) * p.H + y) * p.W + x) * 16) = v;
+                        *reinterpret_cast<uint4*>(rec) = v;                               // slots 0..7
+                        uint2 u;
+                        u.x = pack_half2_sat(hi[0], hi[1]);
+                        u.y = pack_half2_sat(hi[2], hi[3]);
+                        *reinterpret_cast<uint2*>(rec + 12) = u;                          // slots 12..15
+                    }
+                }
+                if (sc.kind != STEP_NONE && p.head.amax_out != nullptr) {
+                    // per-patch max|x_next| for the next call's range scale (non-negative floats order like uints)
+                    const uint32_t key = live ? static_cast<uint32_t>(n) : 0xFFFFFFFFu;
+                    const uint32_t key0 = __shfl_sync(0xffffffffu, key, 0);
+                    const uint32_t bits = __float_as_uint(amax);
+                    if (__all_sync(0xffffffffu, key == key0)) {
+                        const uint32_t mx = __reduce_max_sync(0xffffffffu, bits);
+                        if (lane == 0 && key0 != 0xFFFFFFFFu) atomicMax(p.head.amax_out + key0, mx);
+                    } else if (live) {
+                        atomicMax(p.head.amax_out + n, bits);
                     }
                 }
             } else {
@@ -303,6 +365,9 @@ __global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant
                     dst_px = p.out + ((static_cast<size_t>(n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.out_cpitch +
                              n_tile * BLOCK_N;
                 }
+                const bool first = (p.flags & LAYER_FLAG_FIRST) != 0;
+                const float s_bias = first ? 1.f : s_dn;      // first layer: unscaled inputs, scale the result
+                const float s_post = first ? s_dn : 1.f;
 #pragma unroll
                 for (int c = 0; c < BLOCK_N / 32; ++c) {
                     uint32_t r[32];
@@ -311,9 +376,10 @@ __global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant
                     uint32_t h[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        float a = __uint_as_float(r[2 * j]) + bias_t[c * 32 + 2 * j];
-                        float b = __uint_as_float(r[2 * j + 1]) + bias_t[c * 32 + 2 * j + 1];
+                        float a = fmaf(bias_t[c * 32 + 2 * j], s_bias, __uint_as_float(r[2 * j]));
+                        float b = fmaf(bias_t[c * 32 + 2 * j + 1], s_bias, __uint_as_float(r[2 * j + 1]));
                         if constexpr (MODE != MODE_CONVT) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                        if constexpr (MODE == MODE_STORE) { a *= s_post; b *= s_post; }
                         h[j] = pack_half2_sat(a, b);
                     }
                     __half* dst;
@@ -343,7 +409,7 @@ __global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) mbar_arrive_cluster(tempty_leader);
             }
             acc ^= 1;
             if (acc == 0) acc_ph ^= 1;
@@ -352,9 +418,10 @@ __global__ void __launch_bounds__(256, 1) conv_umma_kernel(const __grid_constant
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                         // both CTAs are done with each other's shared memory and TMEM
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        tmem_dealloc_pair<512>(tmem_base);
     }
 }
 

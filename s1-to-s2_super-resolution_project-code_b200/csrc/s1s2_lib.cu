@@ -48,35 +48,44 @@ void set_err(std::string* dst, const char* fmt, ...) {
 
 // ---------------------------------------------------------------------------------------------- small kernels
 // Input assembly (replaces t_idx.view.float.repeat + 2x torch.cat, DDIM_Multi-step.py:44-45,131):
-// NCHW f32 -> NHWC16 fp16 pixel record [x0 x1 x2 x3 | t t 0 0 | c0 c1 c2 c3 | 0 0 0 0].  The timestep rides in two
-// planes because its weight is split into an fp16 hi/lo pair (exact t up to 2048, weight error 2^-22 instead of 2^-11).
-__global__ void pack_input_kernel(const float* __restrict__ x, size_t x_bstride, const float* __restrict__ cond,
-                                  size_t c_bstride, const int64_t* __restrict__ t_idx, float t_const, float scale,
-                                  float* __restrict__ state, __half* __restrict__ xin16, int HW, size_t total) {
-    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    if (i >= total) return;
-    const int b = static_cast<int>(i / HW);
-    const int pix = static_cast<int>(i - static_cast<size_t>(b) * HW);
-    const float t = t_idx != nullptr ? static_cast<float>(t_idx[b]) : t_const;
-    float xv[4], cv[4];
+// NCHW f32 -> NHWC16 fp16 pixel record [xlo0..3 | t t 0 0 | c0 c1 c2 c3 | xhi0..3].  x_t rides as an fp16 hi/lo pair
+// (x = 4096*hi + lo: ~22 significant bits, range 2.7e8) and so does the WEIGHT of the time plane (exact t up to 2048,
+// weight error 2^-22 instead of 2^-11).  Also records max|x_t| per patch for the range scale of this call.
+__global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, size_t x_bstride,
+                                                         const float* __restrict__ cond, size_t c_bstride,
+                                                         const int64_t* __restrict__ t_idx, float t_const, float scale,
+                                                         float* __restrict__ state, __half* __restrict__ xin16,
+                                                         uint32_t* __restrict__ amax, int HW, size_t total) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;   // HW % 256 == 0: one patch per block
+    const int b = static_cast<int>((blockIdx.x * static_cast<size_t>(blockDim.x)) / HW);
+    float mx = 0.f;
+    if (i < total) {
+        const int pix = static_cast<int>(i - static_cast<size_t>(b) * HW);
+        const float t = t_idx != nullptr ? static_cast<float>(t_idx[b]) : t_const;
+        float xv[4], cv[4], hi[4], lo[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        xv[k] = __fmul_rn(x[b * x_bstride + static_cast<size_t>(k) * HW + pix], scale);
-        cv[k] = cond[b * c_bstride + static_cast<size_t>(k) * HW + pix];
-        if (state != nullptr) state[(static_cast<size_t>(b) * 4 + k) * HW + pix] = xv[k];
+        for (int k = 0; k < 4; ++k) {
+            xv[k] = __fmul_rn(x[b * x_bstride + static_cast<size_t>(k) * HW + pix], scale);
+            cv[k] = cond[b * c_bstride + static_cast<size_t>(k) * HW + pix];
+            if (state != nullptr) state[(static_cast<size_t>(b) * 4 + k) * HW + pix] = xv[k];
+            split_x(xv[k], hi[k], lo[k]);
+            mx = fmaxf(mx, fabsf(xv[k]));
+        }
+        uint4 lo4, hi4;
+        lo4.x = pack_half2_sat(lo[0], lo[1]);
+        lo4.y = pack_half2_sat(lo[2], lo[3]);
+        lo4.z = pack_half2_sat(t, t);
+        lo4.w = 0u;
+        hi4.x = pack_half2_sat(cv[0], cv[1]);
+        hi4.y = pack_half2_sat(cv[2], cv[3]);
+        hi4.z = pack_half2_sat(hi[0], hi[1]);
+        hi4.w = pack_half2_sat(hi[2], hi[3]);
+        uint4* dst = reinterpret_cast<uint4*>(xin16 + i * 16);
+        dst[0] = lo4;
+        dst[1] = hi4;
     }
-    uint4 lo, hi;
-    lo.x = pack_half2_sat(xv[0], xv[1]);
-    lo.y = pack_half2_sat(xv[2], xv[3]);
-    lo.z = pack_half2_sat(t, t);
-    lo.w = 0u;
-    hi.x = pack_half2_sat(cv[0], cv[1]);
-    hi.y = pack_half2_sat(cv[2], cv[3]);
-    hi.z = 0u;
-    hi.w = 0u;
-    uint4* dst = reinterpret_cast<uint4*>(xin16 + i * 16);
-    dst[0] = lo;
-    dst[1] = hi;
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+    if ((threadIdx.x & 31) == 0 && wmax != 0u) atomicMax(amax + b, wmax);
 }
 
 // Conv2d weight OIHW f32 -> [cout][tap][cin] fp16 (K-major rows for the UMMA B operand).
@@ -99,7 +108,8 @@ __global__ void repack_inc_kernel(const float* __restrict__ w, __half* __restric
         const int co = i / (16 * 9);
         auto W = [&](int ci) { return w[(static_cast<size_t>(co) * 9 + ci) * 9 + tap]; };
         float v = 0.f;
-        if (slot < 4) v = W(slot);                       // x_t
+        if (slot < 4) v = W(slot);                       // x_t, lo part
+        else if (slot >= 12) v = __half2float(__float2half_rn(W(slot - 12))) * kXSplit;            // x_t, hi part
         else if (slot == 4) v = __half2float(__float2half_rn(W(8)));                               // t, hi part
         else if (slot == 5) v = W(8) - __half2float(__float2half_rn(W(8)));                        // t, lo part
         else if (slot >= 8 && slot < 12) v = W(4 + slot - 8);                                      // cond
@@ -177,12 +187,12 @@ const KernelInfo* kernel_table() {
     static bool init = false;
     if (!init) {
         t[K_INC] = make_kernel<96, 16, 3, 4, MODE_STORE>();     // Cin = 16-channel pixel record
-        t[K_C96IN] = make_kernel<192, 32, 3, 3, MODE_STORE>();  // Cin = 96 (64-byte swizzle rows)
-        t[K_STORE] = make_kernel<192, 64, 1, 5, MODE_STORE>();
-        t[K_POOL] = make_kernel<192, 64, 1, 5, MODE_POOL>();
-        t[K_CONVT] = make_kernel<192, 64, 1, 5, MODE_CONVT>();
-        t[K_N96] = make_kernel<96, 64, 1, 7, MODE_STORE>();     // Cout = 96
-        t[K_HEAD] = make_kernel<96, 32, 3, 5, MODE_HEAD>();     // conv1.2 + outc + scheduler
+        t[K_C96IN] = make_kernel<192, 32, 3, 5, MODE_STORE>();  // Cin = 96 (64-byte swizzle rows)
+        t[K_STORE] = make_kernel<192, 64, 1, 7, MODE_STORE>();
+        t[K_POOL] = make_kernel<192, 64, 1, 7, MODE_POOL>();
+        t[K_CONVT] = make_kernel<192, 64, 1, 7, MODE_CONVT>();
+        t[K_N96] = make_kernel<96, 64, 1, 9, MODE_STORE>();     // Cout = 96
+        t[K_HEAD] = make_kernel<96, 32, 3, 6, MODE_HEAD>();     // conv1.2 + outc + scheduler
         init = true;
     }
     return t;
@@ -224,6 +234,7 @@ struct s1s2_handle {
     std::vector<Layer> layers;
     std::vector<View> views;
     __half* xin16 = nullptr;
+    uint32_t* amax = nullptr;     // [2][max_batch] float bits of max|x_t| per patch, ping-pong across model calls
     float head_w[kHeadOut * kHeadIn];
     float head_b[kHeadOut];
     // staging for s1s2_sample_host
@@ -297,7 +308,7 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
         const int ktot = L.taps_w * L.taps_w * L.cin;
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(L.ntot)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
-        cuuint32_t box[2] = {static_cast<cuuint32_t>(k.kbox), static_cast<cuuint32_t>(k.block_n)};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(k.kbox), static_cast<cuuint32_t>(k.block_n / 2)};   // per CTA of the pair
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&p.tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L.w, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(k.kbox), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -322,24 +333,27 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
     p.taps_w = L.taps_w;
     p.chunks = L.cin / k.kbox;
     p.cout = L.cout;
+    p.flags = L.kid == K_INC ? LAYER_FLAG_FIRST : 0;
     return S1S2_OK;
 }
 
-int launch_layer(s1s2_handle* h, Layer& L, int B, cudaStream_t st, std::string* err) {
+int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, cudaStream_t st, std::string* err) {
     const KernelInfo& k = kernel_table()[L.kid];
     ConvParams& p = L.p;
     const int tn = 128 >> (p.tw_log2 + p.th_log2);
     p.B = B;
     p.num_m_tiles = p.tiles_x * p.tiles_y * ((B + tn - 1) / tn);
-    const int tiles = p.num_m_tiles * p.num_n_tiles;
-    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-    k.fn<<<grid, 256, k.smem, st>>>(p);
+    p.amax_in = amax_in;
+    const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;      // one CTA pair per (2 M tiles, 1 N tile)
+    const int clusters = pair_tiles < h->num_sms / 2 ? pair_tiles : h->num_sms / 2;
+    k.fn<<<2 * clusters, 256, k.smem, st>>>(p);                            // __cluster_dims__(2, 1, 1)
     CK(cudaGetLastError());
     ++h->launches;
     return S1S2_OK;
 }
 
-int run_network(s1s2_handle* h, int B, const HeadParams& head_io, cudaStream_t st, std::string* err) {
+int run_network(s1s2_handle* h, int B, const HeadParams& head_io, const uint32_t* amax_in, cudaStream_t st,
+                std::string* err) {
     for (size_t i = 0; i < h->layers.size(); ++i) {
         Layer& L = h->layers[i];
         if (L.kid == K_HEAD) {
@@ -350,9 +364,10 @@ int run_network(s1s2_handle* h, int B, const HeadParams& head_io, cudaStream_t s
             hp.pred_out = head_io.pred_out;
             hp.noise = head_io.noise;
             hp.xin16 = head_io.xin16;
+            hp.amax_out = head_io.amax_out;
             hp.step = head_io.step;
         }
-        int rc = launch_layer(h, L, B, st, err);
+        int rc = launch_layer(h, L, B, amax_in, st, err);
         if (rc != S1S2_OK) return rc;
     }
     return S1S2_OK;
@@ -443,6 +458,12 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
         }
         cudaMemset(p, 0, b.elems * sizeof(__half));
         *b.p = static_cast<__half*>(p);
+    }
+    {
+        void* p = nullptr;
+        if (dmalloc(h, &p, sizeof(uint32_t) * 2 * max_batch, err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
+        cudaMemset(p, 0, sizeof(uint32_t) * 2 * max_batch);
+        h->amax = static_cast<uint32_t*>(p);
     }
     {
         const size_t img = static_cast<size_t>(max_batch) * 4 * P0 * sizeof(float);
@@ -587,16 +608,17 @@ int s1s2_forward(s1s2_handle* h, const float* xt_and_cond, const int64_t* t_idx,
     CK(cudaSetDevice(h->device));
     const int HW = h->H * h->W;
     const size_t total = static_cast<size_t>(B) * HW;
+    CK(cudaMemsetAsync(h->amax, 0, sizeof(uint32_t) * B, st));
     pack_input_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
         xt_and_cond, static_cast<size_t>(8) * HW, xt_and_cond + static_cast<size_t>(4) * HW, static_cast<size_t>(8) * HW,
-        t_idx, 0.f, 1.f, nullptr, h->xin16, HW, total);
+        t_idx, 0.f, 1.f, nullptr, h->xin16, h->amax, HW, total);
     CK(cudaGetLastError());
     ++h->launches;
     HeadParams io;
     memset(&io, 0, sizeof(io));
     io.pred_out = out;
     io.step.kind = STEP_NONE;
-    return run_network(h, B, io, st, err);
+    return run_network(h, B, io, h->amax, st, err);
 }
 
 int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond, const float* x_init,
@@ -628,14 +650,19 @@ int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float
     const int HW = h->H * h->W;
     const size_t total = static_cast<size_t>(B) * HW;
     const size_t img = static_cast<size_t>(B) * 4 * HW;
+    CK(cudaMemsetAsync(h->amax, 0, sizeof(uint32_t) * B, st));
     pack_input_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
         x_init, static_cast<size_t>(4) * HW, cond, static_cast<size_t>(4) * HW, nullptr, static_cast<float>(steps[0].t),
-        init_scale, out, h->xin16, HW, total);
+        init_scale, out, h->xin16, h->amax, HW, total);
     CK(cudaGetLastError());
     ++h->launches;
     for (int i = 0; i < n_steps; ++i) {
+        uint32_t* amax_cur = h->amax + static_cast<size_t>(i & 1) * h->max_batch;
+        uint32_t* amax_nxt = h->amax + static_cast<size_t>((i + 1) & 1) * h->max_batch;
+        CK(cudaMemsetAsync(amax_nxt, 0, sizeof(uint32_t) * B, st));   // last read by the previous call, now complete
         HeadParams io;
         memset(&io, 0, sizeof(io));
+        io.amax_out = amax_nxt;
         io.x_t = out;
         io.pred_out = tap_pred != nullptr ? tap_pred + static_cast<size_t>(i) * img : nullptr;
         io.noise = (steps[i].flags & S1S2_STEP_NOISE) ? step_noise + static_cast<size_t>(steps[i].noise_index) * img : nullptr;
@@ -648,7 +675,7 @@ int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float
         io.step.t_next = i + 1 < n_steps ? static_cast<float>(steps[i + 1].t) : 0.f;
         io.step.kind = steps[i].kind;
         io.step.flags = steps[i].flags;
-        rc = run_network(h, B, io, st, err);
+        rc = run_network(h, B, io, amax_cur, st, err);
         if (rc != S1S2_OK) return rc;
         if (tap_x != nullptr)
             CK(cudaMemcpyAsync(tap_x + static_cast<size_t>(i) * img, out, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -732,11 +759,11 @@ int s1s2_profile_layers(s1s2_handle* h, int B, int reps, float* ms_out, int n_ou
                 HeadParams& hp = L.p.head;
                 memcpy(hp.w, h->head_w, sizeof(hp.w));
                 memcpy(hp.b, h->head_b, sizeof(hp.b));
-                hp.x_t = nullptr; hp.pred_out = nullptr; hp.noise = nullptr; hp.xin16 = nullptr;
+                hp.x_t = nullptr; hp.pred_out = nullptr; hp.noise = nullptr; hp.xin16 = nullptr; hp.amax_out = nullptr;
                 hp.step = io.step;
             }
             CK(cudaEventRecord(ev[r * (nl + 1) + i], st));
-            rc = launch_layer(h, L, B, st, err);
+            rc = launch_layer(h, L, B, nullptr, st, err);
             if (rc != S1S2_OK) return rc;
         }
         CK(cudaEventRecord(ev[r * (nl + 1) + nl], st));

@@ -41,9 +41,9 @@ def layer_reference(sd, kind, prefix, inputs):
     x = torch.cat([i.to(torch.float64) for i in inputs], dim=1)
     w, b = sd[prefix + ".weight"], sd[prefix + ".bias"].to(torch.float64)
     if kind == "inc":
-        # pixel record: [x0..x3 | t t 0 0 | c0..c3 | 0 0 0 0]; the t weight is an fp16 hi+lo pair
+        # pixel record: [xlo0..3 | t t 0 0 | c0..c3 | xhi0..3], x = 4096*hi + lo; the t weight is an fp16 hi+lo pair
         rec = x
-        xin = torch.cat([rec[:, 0:4], rec[:, 8:12], rec[:, 4:5]], dim=1)
+        xin = torch.cat([4096.0 * rec[:, 12:16] + rec[:, 0:4], rec[:, 8:12], rec[:, 4:5]], dim=1)
         w64 = h16(w)
         hi = w[:, 8].to(torch.float16).to(torch.float32)
         lo = (w[:, 8] - hi).to(torch.float16).to(torch.float32)
