@@ -120,6 +120,11 @@ int s1s2_debug_activation(s1s2_handle* h, const char* name, float* out_nchw, int
  * milliseconds (ms_out[i], i < n_out; launch order = the network's execution order, see s1s2_layer_name).  Host-
  * synchronous.  Returns the number of launches per model call through *n_layers. */
 int s1s2_profile_layers(s1s2_handle* h, int B, int reps, float* ms_out, int n_out, int* n_layers, void* stream);
+/* Measurement aid: launches layer `layer` alone `reps` times back to back at batch B (event-timed on `stream`, host-
+ * synchronous) and returns the mean milliseconds per launch.  perf_mode bit 0 / bit 1 stop the kernel from re-loading
+ * the activation / weight operand once its shared-memory ring is full, to attribute time to data movement; the
+ * arena contents are garbage afterwards when perf_mode != 0. */
+int s1s2_debug_loop_layer(s1s2_handle* h, int B, int layer, int reps, int perf_mode, float* ms_out, void* stream);
 /* state_dict prefix of the i-th launch of a model call ("inc.0", "down1.0.0", ... "conv1.2"), NULL past the end. */
 const char* s1s2_layer_name(const s1s2_handle* h, int i);
 

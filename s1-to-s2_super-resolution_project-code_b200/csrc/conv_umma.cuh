@@ -81,6 +81,8 @@ struct ConvParams {
     int chunks;                   // K chunks of KBOX channels per tap
     int cout;                     // real channels per output pixel (CONVT: per tap)
     int flags;                    // LAYER_FLAG_*
+    int perf_mode;                // measurement aid (s1s2_debug_loop_layer): bit 0 / bit 1 = stop re-loading A / B
+                                  // once every ring slot has been filled (results are garbage, timing is not)
     HeadParams head;              // MODE_HEAD only
 };
 
@@ -174,49 +176,66 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Both issue loops below run WARP-UNIFORM (all 32 lanes wait on the barriers and keep the loop state; one
+    // elected lane issues TMA / MMA / commit).  Uniform control flow lets ptxas keep descriptors and addresses in
+    // uniform registers; a `lane == 0` branch around the loops instead costs an R2UR + ELECT + BRA.U.ANY sequence
+    // per instruction and made the single issuing thread the bottleneck (~600 cycles per 4-MMA stage).
     if (warp == 0) {
         // ================================================================= TMA producer (both CTAs)
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int n_tile = tile % p.num_n_tiles;
-                const int m_tile = 2 * (tile / p.num_n_tiles) + static_cast<int>(rank);
-                const int tx = m_tile % p.tiles_x;
-                const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-                const int tn = m_tile / (p.tiles_x * p.tiles_y);
-                const int x0 = tx << p.tw_log2;
-                const int y0 = ty << p.th_log2;
-                const int n0 = tn << (7 - p.tw_log2 - p.th_log2);    // past the batch for a phantom tile: zero fill
-                const int b_row0 = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
-                int box = 0;
-                for (int it = 0; it < k_iters; ++it) {
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[s]), 0);
-                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * L::kStage);
-                    uint8_t* a_dst = stage_base + s * L::kStage;
-                    uint8_t* b_dst = a_dst + BOXES * L::kABox;
+        int s = 0;
+        uint32_t ph = 0;
+        int issued = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int n_tile = tile % p.num_n_tiles;
+            const int m_tile = 2 * (tile / p.num_n_tiles) + static_cast<int>(rank);
+            const int tx = m_tile % p.tiles_x;
+            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+            const int tn = m_tile / (p.tiles_x * p.tiles_y);
+            const int x0 = (tx << p.tw_log2) - pad;
+            const int y0 = (ty << p.th_log2) - pad;
+            const int n0 = tn << (7 - p.tw_log2 - p.th_log2);    // past the batch for a phantom tile: zero fill
+            const int b_row0 = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+            int chunk = 0, kx = 0, ky = 0, kcol = 0;             // running (tap, chunk) position, no divisions
+            for (int it = 0; it < k_iters; ++it, ++issued) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const bool load_a = !((p.perf_mode & 1) && issued >= STAGES);
+                const bool load_b = !((p.perf_mode & 2) && issued >= STAGES);
+                uint8_t* a_dst = stage_base + s * L::kStage;
+                uint8_t* b_dst = a_dst + BOXES * L::kABox;
+                const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[s]), 0);
+                if (elect_one()) {
+                    if (rank == 0)
+                        mbar_expect_tx(&full_bar[s], 2 * BOXES * ((load_a ? L::kABox : 0) + (load_b ? L::kBBox : 0)));
 #pragma unroll
-                    for (int b = 0; b < BOXES; ++b, ++box) {
-                        const int tap = box / p.chunks;
-                        const int chunk = box - tap * p.chunks;
-                        const int ky = tap / p.taps_w;
-                        const int kx = tap - ky * p.taps_w;
-                        tma_load_4d_pair(a_dst + b * L::kABox, &p.tmap_a, full_leader, chunk * KBOX, x0 + kx - pad,
-                                         y0 + ky - pad, n0);
-                        tma_load_2d_pair(b_dst + b * L::kBBox, &p.tmap_b, full_leader, box * KBOX, b_row0);
+                    for (int b = 0; b < BOXES; ++b) {
+                        int c_ = chunk + b, kx_ = kx, ky_ = ky;                  // BOXES <= chunks or chunks == 1
+                        if (p.chunks == 1) { kx_ += b; if (kx_ >= p.taps_w) { kx_ -= p.taps_w; ++ky_; } c_ = 0; }
+                        if (load_a)
+                            tma_load_4d_pair(a_dst + b * L::kABox, &p.tmap_a, full_leader, c_ * KBOX, x0 + kx_, y0 + ky_, n0);
+                        if (load_b)
+                            tma_load_2d_pair(b_dst + b * L::kBBox, &p.tmap_b, full_leader, kcol + b * KBOX, b_row0);
                     }
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                kcol += BOXES * KBOX;
+                if (p.chunks == 1) {
+                    kx += BOXES;
+                    while (kx >= p.taps_w) { kx -= p.taps_w; ++ky; }
+                } else {
+                    chunk += BOXES;
+                    if (chunk >= p.chunks) { chunk = 0; if (++kx == p.taps_w) { kx = 0; ++ky; } }
+                }
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ================================================================= MMA issuer (leader CTA, one thread)
-        if (rank == 0 && lane == 0) {
+        // ================================================================= MMA issuer (leader CTA)
+        if (rank == 0) {
             int s = 0;
             uint32_t ph = 0;
             int acc = 0;
             uint32_t acc_ph = 0;
+            const uint32_t stage0 = smem_u32(stage_base);
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
                 tc_fence_after();
@@ -224,20 +243,23 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 for (int it = 0; it < k_iters; ++it) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(stage_base + s * L::kStage);
+                    const uint32_t a_addr = stage0 + s * L::kStage;
                     const uint32_t b_addr = a_addr + BOXES * L::kABox;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int b = 0; b < BOXES; ++b) {
-                        const uint64_t adesc = umma_smem_desc<kRowBytes>(a_addr + b * L::kABox);
-                        const uint64_t bdesc = umma_smem_desc<kRowBytes>(b_addr + b * L::kBBox);
+                        for (int b = 0; b < BOXES; ++b) {
+                            const uint64_t adesc = umma_smem_desc<kRowBytes>(a_addr + b * L::kABox);
+                            const uint64_t bdesc = umma_smem_desc<kRowBytes>(b_addr + b * L::kBBox);
 #pragma unroll
-                        for (int k = 0; k < KBOX / 16; ++k) {
-                            // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
-                            umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (it | b | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < KBOX / 16; ++k) {
+                                // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
+                                umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (it | b | k) != 0 ? 1u : 0u);
+                            }
                         }
+                        umma_commit_pair(&empty_bar[s]);        // both CTAs' slots reusable once these MMAs retire
+                        if (it == k_iters - 1) umma_commit_pair(&tfull_bar[acc]);
                     }
-                    umma_commit_pair(&empty_bar[s]);            // both CTAs' slots reusable once these MMAs retire
-                    if (it == k_iters - 1) umma_commit_pair(&tfull_bar[acc]);
+                    __syncwarp();
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 acc ^= 1;

@@ -282,7 +282,9 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
     }
     const int Hl = h->H >> L.level, Wl = h->W >> L.level;
     const TileGeom g = tile_geom(Hl, Wl);
-    if (L.cin % k.kbox != 0 || (L.taps_w * L.taps_w * (L.cin / k.kbox)) % k.boxes != 0 || L.ntot % k.block_n != 0) {
+    const int chunks_ = L.cin / k.kbox;
+    const bool boxes_ok = chunks_ == 1 ? (L.taps_w * L.taps_w) % k.boxes == 0 : chunks_ % k.boxes == 0;
+    if (L.cin % k.kbox != 0 || !boxes_ok || L.ntot % k.block_n != 0) {
         set_err(err, "layer %s: geometry does not fit kernel (cin %d, N %d)", L.name, L.cin, L.ntot);
         return S1S2_ERR_INVALID;
     }
@@ -734,6 +736,43 @@ const char* s1s2_layer_name(const s1s2_handle* h, int i) {
     return h->layers[i].name;
 }
 
+int s1s2_debug_loop_layer(s1s2_handle* h, int B, int layer, int reps, int perf_mode, float* ms_out, void* stream) {
+    int rc = check_batch(h, B);
+    if (rc != S1S2_OK) return rc;
+    std::string* err = &h->err;
+    if (layer < 0 || layer >= static_cast<int>(h->layers.size()) || reps < 1 || ms_out == nullptr) {
+        set_err(err, "s1s2_debug_loop_layer: layer %d, reps %d", layer, reps);
+        return S1S2_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    Layer& L = h->layers[layer];
+    if (L.kid == K_HEAD) {
+        HeadParams& hp = L.p.head;
+        memcpy(hp.w, h->head_w, sizeof(hp.w));
+        memcpy(hp.b, h->head_b, sizeof(hp.b));
+        hp.x_t = nullptr; hp.pred_out = nullptr; hp.noise = nullptr; hp.xin16 = nullptr; hp.amax_out = nullptr;
+        hp.step.kind = STEP_NONE;
+    }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    L.p.perf_mode = perf_mode;
+    rc = launch_layer(h, L, B, nullptr, st, err);      // warm-up
+    CK(cudaEventRecord(e0, st));
+    for (int r = 0; r < reps && rc == S1S2_OK; ++r) rc = launch_layer(h, L, B, nullptr, st, err);
+    CK(cudaEventRecord(e1, st));
+    L.p.perf_mode = 0;
+    if (rc != S1S2_OK) return rc;
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return S1S2_OK;
+}
+
 int s1s2_profile_layers(s1s2_handle* h, int B, int reps, float* ms_out, int n_out, int* n_layers, void* stream) {
     int rc = check_batch(h, B);
     if (rc != S1S2_OK) return rc;
@@ -785,6 +824,7 @@ int s1s2_profile_layers(s1s2_handle* h, int B, int reps, float* ms_out, int n_ou
 int s1s2_tile_extract(int device, const float* scene, const uint8_t* vmask, int SH, int SW, const int32_t* origins, int N,
                       int ps, float* cond, uint8_t* mask, float* valid_ratio, void* stream) {
     std::string* err = &g_error;
+    if (N == 0) return S1S2_OK;
     if (scene == nullptr || origins == nullptr || cond == nullptr || mask == nullptr || N < 0 || ps < 1 || ps > SH || ps > SW) {
         set_err(err, "s1s2_tile_extract: bad argument (N %d, ps %d, scene %d x %d)", N, ps, SH, SW);
         return S1S2_ERR_INVALID;

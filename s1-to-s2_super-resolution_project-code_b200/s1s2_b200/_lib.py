@@ -43,6 +43,7 @@ SIGNATURES = {
                                         C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     "s1s2_profile_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int),
                                       C.c_void_p]),
+    "s1s2_debug_loop_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "s1s2_layer_name": (C.c_char_p, [C.c_void_p, C.c_int]),
     "s1s2_tile_extract": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

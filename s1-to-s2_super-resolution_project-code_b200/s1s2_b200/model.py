@@ -118,6 +118,14 @@ class UNetSmallB200(nn.Module):
         _lib.check(L.s1s2_profile_layers(eng.h, batch, reps, ms, n.value, C.byref(n), C.c_void_p(stream)), eng.h)
         return [(L.s1s2_layer_name(eng.h, i).decode(), float(ms[i])) for i in range(n.value)]
 
+    def loop_layer(self, device, H: int, W: int, batch: int, layer: int, reps: int, perf_mode: int = 0) -> float:
+        """Mean ms per launch of one layer run alone `reps` times (s1s2_debug_loop_layer; measurement aid)."""
+        eng = self.engine(torch.device(device), H, W, batch)
+        ms = C.c_float()
+        stream = torch.cuda.current_stream(torch.device(device)).cuda_stream
+        _lib.check(_lib.lib().s1s2_debug_loop_layer(eng.h, batch, layer, reps, perf_mode, C.byref(ms), C.c_void_p(stream)), eng.h)
+        return float(ms.value)
+
     # ------------------------------------------------------------------ the reference's call
     @torch.no_grad()
     def forward(self, xt_and_cond: torch.Tensor, t_idx: torch.Tensor) -> torch.Tensor:

@@ -56,5 +56,32 @@ def main():
               f"{B/(ms/1e3)*len(steps)/50:.2f} DDIM-50-equivalent patches/s", flush=True)
 
 
+def loop_mode():
+    """python tools/diag.py loop B layer_idx[,layer_idx..] reps : each layer alone, perf modes 0..3, with clocks."""
+    import subprocess
+    sys.path.insert(0, ROOT)
+    import bench
+    B, reps = int(sys.argv[2]), int(sys.argv[4])
+    layers = [int(v) for v in sys.argv[3].split(",")]
+    modes = [int(v) for v in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0, 1, 2, 3]
+    sd, m = make(B)
+    fl = bench.layer_flops()
+    m(torch.randn((B, 8, 256, 256), device="cuda"), torch.zeros(B, dtype=torch.long, device="cuda"))
+    torch.cuda.synchronize()
+    for li in layers:
+        for mode in modes:
+            cs = bench.ClockSampler(0)
+            ms = m.loop_layer("cuda", 256, 256, B, li, reps, mode)
+            clk = cs.stop()
+            tf = fl[li][1] * B / (ms / 1e3) / 1e12
+            mhz = clk.get("sm_mhz") or 0
+            util = tf * 1e12 / (148 * 8192 * mhz * 1e6) if mhz else 0
+            print(f"layer {li:2d} {fl[li][0]:10s} mode {mode}: {ms:7.3f} ms  {tf:7.1f} TFLOP/s  sm {mhz:6.0f} MHz  "
+                  f"util@clk {util:5.3f}  power {clk.get('power_w_max')} reasons {clk.get('reasons')}", flush=True)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "loop":
+        loop_mode()
+        sys.exit(0)
     main()
