@@ -69,6 +69,7 @@ struct HeadParams {
 struct ConvParams {
     CUtensorMap tmap_a;
     CUtensorMap tmap_b;
+    CUtensorMap tmap_out;         // MODE_STORE / MODE_POOL: NHWC destination, box = 32 channels x the (pooled) pixel tile
     const float* bias;            // [num_n_tiles * BLOCK_N]
     const uint32_t* amax_in;      // [B] float bits of max|x_t| per patch for this call (nullptr: scale 1)
     __half* out;                  // NHWC fp16 destination (channel offset already applied)
@@ -86,13 +87,20 @@ struct ConvParams {
     HeadParams head;              // MODE_HEAD only
 };
 
-template <int BLOCK_N, int KBOX, int BOXES, int STAGES>
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE>
 struct ConvSmem {
     static constexpr int kABox = 128 * KBOX * 2;
     static constexpr int kBBox = (BLOCK_N / 2) * KBOX * 2;      // this CTA's half of the weight rows
     static constexpr int kStage = BOXES * (kABox + kBBox);
+    // output staging for the TMA store: one [rows][32 channels] fp16 sub-tile (64-byte rows, 64B swizzle) per
+    // 32-column accumulator chunk; rows = 128 pixels, or the 32 pooled pixels of the tile
+    static constexpr int kSubRows = MODE == MODE_POOL ? 32 : 128;
+    static constexpr int kSubBytes = kSubRows * 64;
+    static constexpr int kStaging = (MODE == MODE_STORE || MODE == MODE_POOL) ? (BLOCK_N / 32) * kSubBytes : 0;
     static constexpr int kBias = 1536 * 4;
-    static constexpr int kBytes = 1024 /*align slack*/ + STAGES * kStage + kBias + 256 /*barriers*/;
+    static constexpr int kBytes = 1024 /*align slack*/ + STAGES * kStage + kStaging + kBias + 256 /*barriers*/;
+    static_assert(kStage % 512 == 0, "stage alignment");
+    static_assert(kBytes <= 232448, "shared memory budget");
 };
 
 __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
@@ -122,7 +130,8 @@ __device__ __forceinline__ float range_scale(uint32_t amax_bits, float& s) {
 template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
-    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES>;
+    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE>;
+    constexpr bool kTmaStore = (MODE == MODE_STORE || MODE == MODE_POOL);
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
     static_assert(KBOX == 16 || KBOX == 32 || KBOX == 64, "KBOX");
     constexpr int kRowBytes = KBOX * 2;
@@ -132,8 +141,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
-    float* sbias = reinterpret_cast<float*>(smem + STAGES * L::kStage);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage + L::kBias);
+    uint8_t* sout = smem + STAGES * L::kStage;
+    float* sbias = reinterpret_cast<float*>(smem + STAGES * L::kStage + L::kStaging);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage + L::kStaging + L::kBias);
     uint64_t* full_bar = bars;                    // [STAGES]   (leader's copy is the live one)
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]   (one per CTA, signalled by multicast commits)
     uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]        (one per CTA, multicast commits)
@@ -153,6 +163,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmap_a);
         tma_prefetch_desc(&p.tmap_b);
+        if constexpr (kTmaStore) tma_prefetch_desc(&p.tmap_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -377,15 +388,20 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     }
                 }
             } else {
-                // destination pixel row (channel 0 of this N tile / tap), resolved per chunk for CONVT
-                __half* dst_px = nullptr;
-                bool writer = live;
-                if constexpr (MODE == MODE_STORE) {
-                    dst_px = p.out + ((static_cast<size_t>(n) * p.H + y) * p.W + x) * p.out_cpitch + n_tile * BLOCK_N;
-                } else if constexpr (MODE == MODE_POOL) {
-                    writer = live && ((lx | ly) & 1) == 0;
-                    dst_px = p.out + ((static_cast<size_t>(n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.out_cpitch +
-                             n_tile * BLOCK_N;
+                // STORE / POOL: the tile is staged in shared memory ([row][32 ch] sub-tiles, 64B swizzle) and leaves
+                // through TMA stores (full-sector, asynchronous, clipped at the image / batch border).
+                // CONVT: direct stores to the (2y+ky, 2x+kx) pixels of the tap this 32-column chunk belongs to.
+                int srow = m;                                  // staging row of this thread's pixel
+                bool writer = true;
+                if constexpr (MODE == MODE_POOL) {
+                    writer = ((lx | ly) & 1) == 0;
+                    srow = ((ln << (p.th_log2 - 1)) + (ly >> 1)) * (tw >> 1) + (lx >> 1);
+                } else if constexpr (MODE == MODE_CONVT) {
+                    writer = live;
+                }
+                if constexpr (kTmaStore) {
+                    if (warp == 4 && lane == 0) bulk_wait_read0();      // previous tile's stores have read the staging
+                    named_bar_sync(1, 128);
                 }
                 const bool first = (p.flags & LAYER_FLAG_FIRST) != 0;
                 const float s_bias = first ? 1.f : s_dn;      // first layer: unscaled inputs, scale the result
@@ -404,40 +420,62 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                         if constexpr (MODE == MODE_STORE) { a *= s_post; b *= s_post; }
                         h[j] = pack_half2_sat(a, b);
                     }
-                    __half* dst;
                     if constexpr (MODE == MODE_POOL) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             h[j] = hmax2_u32(h[j], __shfl_xor_sync(0xffffffffu, h[j], 1));
                             h[j] = hmax2_u32(h[j], __shfl_xor_sync(0xffffffffu, h[j], tw));
                         }
-                        dst = dst_px + c * 32;
-                    } else if constexpr (MODE == MODE_CONVT) {
+                    }
+                    if constexpr (kTmaStore) {
+                        if (writer) {
+                            uint8_t* row = sout + c * L::kSubBytes + srow * 64;
+                            const int sw = (srow >> 1) & 3;                            // 64B swizzle: chunk ^= row[2:1]
+                            *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+                            *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+                            *reinterpret_cast<uint4*>(row + ((2 ^ sw) << 4)) = make_uint4(h[8], h[9], h[10], h[11]);
+                            *reinterpret_cast<uint4*>(row + ((3 ^ sw) << 4)) = make_uint4(h[12], h[13], h[14], h[15]);
+                        }
+                    } else {
                         const int ng = n_tile * BLOCK_N + c * 32;
                         const int tap = ng / p.cout;
                         const int co = ng - tap * p.cout;
                         const int oy = 2 * y + (tap >> 1), ox = 2 * x + (tap & 1);
-                        dst = p.out + ((static_cast<size_t>(n) * (2 * p.H) + oy) * (2 * p.W) + ox) * p.out_cpitch + co;
-                    } else {
-                        dst = dst_px + c * 32;
-                    }
-                    if (writer) {
-                        uint4* d4 = reinterpret_cast<uint4*>(dst);
-                        d4[0] = make_uint4(h[0], h[1], h[2], h[3]);
-                        d4[1] = make_uint4(h[4], h[5], h[6], h[7]);
-                        d4[2] = make_uint4(h[8], h[9], h[10], h[11]);
-                        d4[3] = make_uint4(h[12], h[13], h[14], h[15]);
+                        __half* dst = p.out + ((static_cast<size_t>(n) * (2 * p.H) + oy) * (2 * p.W) + ox) * p.out_cpitch + co;
+                        if (writer) {
+                            uint4* d4 = reinterpret_cast<uint4*>(dst);
+                            d4[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                            d4[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                            d4[2] = make_uint4(h[8], h[9], h[10], h[11]);
+                            d4[3] = make_uint4(h[12], h[13], h[14], h[15]);
+                        }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tempty_leader);
+                if constexpr (kTmaStore) {
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (warp == 4 && lane == 0) {
+                        const int sh = MODE == MODE_POOL ? 1 : 0;
+                        const int ox0 = (tx << p.tw_log2) >> sh, oy0 = (ty << p.th_log2) >> sh;
+                        const int on0 = tn << (7 - p.tw_log2 - p.th_log2);
+#pragma unroll
+                        for (int c = 0; c < BLOCK_N / 32; ++c)
+                            tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, n_tile * BLOCK_N + c * 32, ox0, oy0, on0);
+                        bulk_commit();
+                    }
+                }
             }
             acc ^= 1;
             if (acc == 0) acc_ph ^= 1;
         }
     }
 
+    if constexpr (kTmaStore) {
+        if (warp == 4 && lane == 0) bulk_wait0();   // all output stores of this CTA have completed
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                         // both CTAs are done with each other's shared memory and TMEM

@@ -164,11 +164,11 @@ CUtensorMapSwizzle swizzle_for(int kbox) {
 }
 
 // ---------------------------------------------------------------------------------------------- layers
-enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_N96, K_HEAD, K_COUNT };
+enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_COUNT };
 
 struct KernelInfo {
     void (*fn)(const ConvParams);
-    int block_n, kbox, boxes, smem;
+    int block_n, kbox, boxes, smem, mode;
 };
 
 template <int BN, int KB, int BX, int ST, int MODE>
@@ -178,7 +178,8 @@ KernelInfo make_kernel() {
     k.block_n = BN;
     k.kbox = KB;
     k.boxes = BX;
-    k.smem = ConvSmem<BN, KB, BX, ST>::kBytes;
+    k.smem = ConvSmem<BN, KB, BX, ST, MODE>::kBytes;
+    k.mode = MODE;
     return k;
 }
 
@@ -186,12 +187,17 @@ const KernelInfo* kernel_table() {
     static KernelInfo t[K_COUNT];
     static bool init = false;
     if (!init) {
+        // UMMA time per instruction is ~128 cycles (one M row per cycle) whatever N <= 256 is, so N = 256 tiles are
+        // used wherever the GEMM N (Cout, or 4*Cout for the transposed convs) is a multiple of 256.
         t[K_INC] = make_kernel<96, 16, 3, 4, MODE_STORE>();     // Cin = 16-channel pixel record
-        t[K_C96IN] = make_kernel<192, 32, 3, 5, MODE_STORE>();  // Cin = 96 (64-byte swizzle rows)
-        t[K_STORE] = make_kernel<192, 64, 1, 7, MODE_STORE>();
+        t[K_C96IN] = make_kernel<192, 32, 3, 4, MODE_STORE>();  // Cin = 96 (64-byte swizzle rows)
+        t[K_STORE] = make_kernel<192, 64, 1, 6, MODE_STORE>();
         t[K_POOL] = make_kernel<192, 64, 1, 7, MODE_POOL>();
         t[K_CONVT] = make_kernel<192, 64, 1, 7, MODE_CONVT>();
-        t[K_N96] = make_kernel<96, 64, 1, 9, MODE_STORE>();     // Cout = 96
+        t[K_STORE256] = make_kernel<256, 64, 1, 4, MODE_STORE>();
+        t[K_POOL256] = make_kernel<256, 64, 1, 6, MODE_POOL>();
+        t[K_CONVT256] = make_kernel<256, 64, 1, 6, MODE_CONVT>();
+        t[K_N96] = make_kernel<96, 64, 1, 8, MODE_STORE>();     // Cout = 96
         t[K_HEAD] = make_kernel<96, 32, 3, 6, MODE_HEAD>();     // conv1.2 + outc + scheduler
         init = true;
     }
@@ -317,6 +323,28 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_err(err, "layer %s: weight tensor map rejected (CUresult %d)", L.name, static_cast<int>(r));
+            return S1S2_ERR_CUDA;
+        }
+    }
+    if (k.mode == MODE_STORE || k.mode == MODE_POOL) {
+        // destination: (C, W, H, N) of the (pooled) output, box = 32 channels x the (pooled) pixel tile, 64B swizzle
+        const int sh = k.mode == MODE_POOL ? 1 : 0;
+        if (sh && (g.tw_log2 < 1 || g.th_log2 < 1)) {
+            set_err(err, "layer %s: pooled tile needs an M tile at least 2 x 2 pixels", L.name);
+            return S1S2_ERR_INVALID;
+        }
+        const int Ho = Hl >> sh, Wo = Wl >> sh;
+        cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.ntot), static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Ho),
+                              static_cast<cuuint64_t>(h->nalloc)};
+        cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.dst_pitch) * 2, static_cast<cuuint64_t>(Wo) * L.dst_pitch * 2,
+                                 static_cast<cuuint64_t>(Ho) * Wo * L.dst_pitch * 2};
+        cuuint32_t box[4] = {32u, (1u << g.tw_log2) >> sh, (1u << g.th_log2) >> sh, static_cast<cuuint32_t>(g.tn)};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&p.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, L.dst, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_err(err, "layer %s: output tensor map rejected (CUresult %d)", L.name, static_cast<int>(r));
             return S1S2_ERR_CUDA;
         }
     }
@@ -491,12 +519,12 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     add("down1.0.2",   K_POOL,   0,  192, 192,  192, 3,   d1a,         192,  cat2 + 192,   384);
     add("down2.0.0",   K_STORE,  1,  192, 384,  384, 3,   cat2 + 192,  384,  d2a,          384);
     add("down2.0.2",   K_POOL,   1,  384, 384,  384, 3,   d2a,         384,  cat3 + 384,   768);
-    add("down3.0.0",   K_STORE,  2,  384, 768,  768, 3,   cat3 + 384,  768,  d3a,          768);
-    add("down3.0.2",   K_POOL,   2,  768, 768,  768, 3,   d3a,         768,  e4,           768);
-    add("up3",         K_CONVT,  3,  768, 1536, 384, 1,   e4,          768,  cat3,         768);
+    add("down3.0.0",   K_STORE256, 2, 384, 768,  768, 3,  cat3 + 384,  768,  d3a,          768);
+    add("down3.0.2",   K_POOL256, 2, 768, 768,  768, 3,   d3a,         768,  e4,           768);
+    add("up3",         K_CONVT256, 3, 768, 1536, 384, 1,  e4,          768,  cat3,         768);
     add("conv3.0",     K_STORE,  2,  768, 384,  384, 3,   cat3,        768,  c3a,          384);
     add("conv3.2",     K_STORE,  2,  384, 384,  384, 3,   c3a,         384,  c3b,          384);
-    add("up2",         K_CONVT,  2,  384, 768,  192, 1,   c3b,         384,  cat2,         384);
+    add("up2",         K_CONVT256, 2, 384, 768,  192, 1,  c3b,         384,  cat2,         384);
     add("conv2.0",     K_STORE,  1,  384, 192,  192, 3,   cat2,        384,  c2a,          192);
     add("conv2.2",     K_STORE,  1,  192, 192,  192, 3,   c2a,         192,  c2b,          192);
     add("up1",         K_CONVT,  1,  192, 384,  96,  1,   c2b,         192,  cat1,         192);
@@ -570,7 +598,7 @@ int s1s2_load_weights(s1s2_handle* h, int n, const char* const* names, const flo
             if ((rc = find(nm + ".weight", 96 * 9 * 9, &w)) || (rc = find(nm + ".bias", 96, &b))) return rc;
             repack_inc_kernel<<<64, 256, 0, st>>>(w, L.w, 96);
             tile_bias_kernel<<<4, 256, 0, st>>>(b, L.bias, 96, 1);
-        } else if (L.kid == K_CONVT) {
+        } else if (kernel_table()[L.kid].mode == MODE_CONVT) {
             if ((rc = find(nm + ".weight", static_cast<int64_t>(L.cin) * L.cout * 4, &w)) ||
                 (rc = find(nm + ".bias", L.cout, &b)))
                 return rc;
