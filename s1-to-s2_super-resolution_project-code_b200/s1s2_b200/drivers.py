@@ -1,0 +1,285 @@
+"""Drop-in command-line drivers with the reference scripts' flags and output files, running on the fused CUDA path.
+
+  python -m s1s2_b200.drivers onestep      ...   Evaluation/Onestep.py:93-175 (and Onestep_v_Prediction.py with --param v)
+  python -m s1s2_b200.drivers ddim         ...   Evaluation/DDIM_Multi-step.py --mode ddim (:173-232)
+  python -m s1s2_b200.drivers ddim_v       ...   Evaluation/DDIM_Multi-step_v_Prediction.py --mode ddim
+  python -m s1s2_b200.drivers ddim_sweep   ...   Evaluation/DDIM_Sweep.py --mode ddim_sweep (:387-416); --param v sweeps the
+                                                 step counts of BASELINE.json's config 4 on the v model
+  python -m s1s2_b200.drivers true_infer   ...   Evaluation_Updated/Evaluation_Pure_Generation.py --mode ddim --true_infer (:539-574)
+  python -m s1s2_b200.drivers scene        ...   whole-scene generation (Patch.py tiling + stitch, s1s2_b200.scene), under torchrun
+
+Same flag names (--patch_dir --ckpt --out_dir --T --base_ch --max_files --t_start --ddim_steps --ddim_eta --t_small
+--n_seeds --seed_base), same CSV / summary column sets.  PNG previews are not produced (visualisation is outside the
+hot path).  Patches are read from Patch.py's `patch_*.npz` files (keys inputs / target / mask, Patch.py:249-255) and
+processed `--batch` at a time; per-patch results do not depend on the batch size.
+"""
+import argparse
+import csv
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import metrics, samplers, schedule
+from .model import UNetSmallB200
+
+
+def load_npz_as_tensors(path, device):
+    """Evaluation/DDIM_Multi-step.py:104-111."""
+    d = np.load(path)
+    x_cond = torch.from_numpy(np.nan_to_num(d["inputs"].astype(np.float32))).unsqueeze(0).to(device)
+    x_gt = torch.from_numpy(np.nan_to_num(d["target"].astype(np.float32))).unsqueeze(0).to(device)
+    mask = torch.from_numpy(np.nan_to_num(d["mask"].astype(np.float32))).unsqueeze(0).to(device) if "mask" in d else None
+    return x_cond, x_gt, mask, x_cond.size(1), x_gt.size(1)
+
+
+def load_model(ckpt, in_ch, out_ch, base_ch, device, max_batch):
+    """Evaluation/DDIM_Multi-step_v_Prediction.py:263-271 (optional {"model"| "state_dict"} wrapper, strict load)."""
+    model = UNetSmallB200(in_ch=in_ch, out_ch=out_ch, base_ch=base_ch, max_batch=max_batch).to(device)
+    state = torch.load(ckpt, map_location=device)
+    if isinstance(state, dict) and "model" in state and isinstance(state["model"], dict):
+        state = state["model"]
+    elif isinstance(state, dict) and "state_dict" in state and isinstance(state["state_dict"], dict):
+        state = state["state_dict"]
+    model.load_state_dict(state, strict=True)
+    return model.eval()
+
+
+def _files(args):
+    files = sorted(f for f in os.listdir(args.patch_dir) if f.endswith(".npz"))
+    assert files, "No .npz found"
+    return files[:args.max_files] if args.max_files > 0 else files
+
+
+def _setup(args):
+    os.makedirs(args.out_dir, exist_ok=True)
+    device = torch.device("cuda")
+    files = _files(args)
+    print(f"[INFO] Evaluating {len(files)} files")
+    x_cond0, x_gt0, _, Cc, Ct = load_npz_as_tensors(os.path.join(args.patch_dir, files[0]), device)
+    model = load_model(args.ckpt, Cc + Ct, Ct, args.base_ch, device, args.batch)
+    _, _, alpha_bar = schedule.derive(schedule.cosine_beta_schedule(args.T))
+    return device, files, model, alpha_bar.to(device)
+
+
+def _batches(args, files, device):
+    for lo in range(0, len(files), args.batch):
+        names = files[lo:lo + args.batch]
+        items = [load_npz_as_tensors(os.path.join(args.patch_dir, f), device) for f in names]
+        cond = torch.cat([it[0] for it in items], 0)
+        gt = torch.cat([it[1] for it in items], 0)
+        mask = [it[2] for it in items]
+        yield lo, names, cond, gt, mask
+
+
+def _mstd(a):
+    t = torch.tensor(a)
+    return t.mean().item(), t.std(unbiased=False).item()
+
+
+def _recon_batch(args, model, alpha_bar, cond, gt, noise, param, t_start, steps):
+    """x0 of the from-noised-GT (eps) / from-noise (v) multistep evaluators for a batch, per-patch noise supplied."""
+    if param == "v":
+        ab = schedule._abar_cpu(alpha_bar)
+        T = len(ab)
+        K = max(1, min(int(t_start), T - 1))
+        st = schedule.steps_grid_b(alpha_bar, schedule.grid_b(K, steps), "v", eta=float(args.ddim_eta))
+        return samplers.run_steps(model, st, cond, noise, init_scale=float(torch.sqrt(1 - ab[K])))
+    t_start = max(1, min(int(t_start), len(alpha_bar) - 1))
+    a_t = alpha_bar[t_start].view(-1, 1, 1, 1)
+    x_t = torch.sqrt(a_t) * gt + torch.sqrt(1 - a_t) * noise
+    return samplers.run_steps(model, schedule.steps_eps_grid_a(alpha_bar, t_start, steps), cond, x_t)
+
+
+def cmd_ddim(args, param):
+    device, files, model, alpha_bar = _setup(args)
+    maes, mses = [], []
+    t0 = time.perf_counter()
+    with open(os.path.join(args.out_dir, "ddim_metrics.csv"), "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["file", "t_start", "ddim_steps", "MAE", "MSE"] if param == "eps" else
+                   ["file", "t_start", "ddim_steps", "eta", "MAE", "MSE"])
+        for lo, names, cond, gt, mask in _batches(args, files, device):
+            noise = torch.cat([torch.randn_like(gt[i:i + 1]) for i in range(len(names))], 0)   # one draw per file
+            x0 = _recon_batch(args, model, alpha_bar, cond, gt, noise, param, args.t_start, args.ddim_steps)
+            for i, fname in enumerate(names):
+                mae = metrics.masked_mae(x0[i:i + 1], gt[i:i + 1], mask[i])
+                mse = metrics.masked_mse(x0[i:i + 1], gt[i:i + 1], mask[i])
+                maes.append(mae); mses.append(mse)
+                row = [fname, args.t_start, args.ddim_steps] + ([args.ddim_eta] if param == "v" else [])
+                w.writerow(row + [f"{mae:.6f}", f"{mse:.6f}"])
+    with open(os.path.join(args.out_dir, "ddim_summary.txt"), "w") as f:
+        f.write(f"files: {len(files)}  t_start: {args.t_start}  steps: {args.ddim_steps}\n")
+        f.write(f"MAE mean/std: {_mstd(maes)[0]:.6f} / {_mstd(maes)[1]:.6f}\n")
+        f.write(f"MSE mean/std: {_mstd(mses)[0]:.6f} / {_mstd(mses)[1]:.6f}\n")
+    print(f"[DONE] DDIM ({len(files) / (time.perf_counter() - t0):.2f} patches/s incl. file I/O)")
+
+
+def cmd_sweep(args):
+    device, files, model, alpha_bar = _setup(args)
+    t_list = [int(x) for x in args.t_start_grid.split(",")]
+    k_list = [int(x) for x in args.ddim_steps_grid.split(",")]
+    with open(os.path.join(args.out_dir, "ddim_sweep_summary.csv"), "w", newline="") as fsum:
+        wsum = csv.writer(fsum)
+        wsum.writerow(["t_start", "steps", "files", "MAE_mean", "MAE_std", "MSE_mean", "MSE_std", "ms_per_step", "patches_per_s"])
+        for t_start in t_list:
+            for steps in k_list:
+                maes, mses, n_calls = [], [], 0
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for lo, names, cond, gt, mask in _batches(args, files, device):
+                    noise = []
+                    for i in range(len(names)):       # same file -> same starting noise across all configs (:404)
+                        torch.manual_seed(args.seed_base + lo + i)
+                        noise.append(torch.randn_like(gt[i:i + 1]))
+                    x0 = _recon_batch(args, model, alpha_bar, cond, gt, torch.cat(noise, 0), args.param, t_start, steps)
+                    n_calls = steps if args.param == "eps" else len(schedule.grid_b(max(1, min(t_start, args.T - 1)), steps))
+                    for i in range(len(names)):
+                        maes.append(metrics.masked_mae(x0[i:i + 1], gt[i:i + 1], mask[i]))
+                        mses.append(metrics.masked_mse(x0[i:i + 1], gt[i:i + 1], mask[i]))
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                nb = (len(files) + args.batch - 1) // args.batch
+                wsum.writerow([t_start, steps, len(files), f"{_mstd(maes)[0]:.6f}", f"{_mstd(maes)[1]:.6f}",
+                               f"{_mstd(mses)[0]:.6f}", f"{_mstd(mses)[1]:.6f}", f"{dt / (nb * max(n_calls, 1)) * 1e3:.3f}",
+                               f"{len(files) / dt:.3f}"])
+    print("[DONE] DDIM sweep")
+
+
+def cmd_true_infer(args):
+    device, files, model, alpha_bar = _setup(args)
+    agg = {k: [] for k in ("mae", "mse", "psnr", "sam", "ergas")}
+    with open(os.path.join(args.out_dir, "ddim_true_infer_metrics.csv"), "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["file", "t_start", "ddim_steps", "seeds", "MAE_mean", "MAE_std", "MSE_mean", "MSE_std", "PSNR_mean",
+                    "SAM_mean", "ERGAS_mean"])
+        for lo, names, cond, gt, mask in _batches(args, files, device):
+            per = [{k: [] for k in agg} for _ in names]
+            for s in range(args.n_seeds):
+                noise = []
+                for i in range(len(names)):           # the reference re-seeds before every generate call (:553)
+                    torch.manual_seed(args.seed_base + s)
+                    noise.append(torch.randn((1, gt.size(1), gt.size(2), gt.size(3)), device=device))
+                x0 = samplers.ddpm_ddim_generate(model, cond, alpha_bar, t_start=args.t_start, steps=args.ddim_steps,
+                                                 noise=torch.cat(noise, 0))
+                for i in range(len(names)):
+                    p, g, m = x0[i:i + 1], gt[i:i + 1], mask[i]
+                    per[i]["mae"].append(metrics.masked_mae(p, g, m)); per[i]["mse"].append(metrics.masked_mse(p, g, m))
+                    per[i]["psnr"].append(metrics.psnr(p, g, m)); per[i]["sam"].append(metrics.sam(p, g, m))
+                    per[i]["ergas"].append(metrics.ergas(p, g, m))
+            for i, fname in enumerate(names):
+                mu = {k: float(np.mean(v)) for k, v in per[i].items()}
+                sd = {k: float(np.std(v, ddof=0)) for k, v in per[i].items()}
+                w.writerow([fname, args.t_start, args.ddim_steps, args.n_seeds, f"{mu['mae']:.6f}", f"{sd['mae']:.6f}",
+                            f"{mu['mse']:.6f}", f"{sd['mse']:.6f}", f"{mu['psnr']:.3f}", f"{mu['sam']:.4f}", f"{mu['ergas']:.2f}"])
+                for k in agg:
+                    agg[k].append(mu[k])
+    with open(os.path.join(args.out_dir, "ddim_true_infer_summary.txt"), "w") as f:
+        f.write(f"files: {len(files)}  t_start: {args.t_start}  steps: {args.ddim_steps}  seeds: {args.n_seeds}\n")
+        f.write(f"MAE mean/std:  {_mstd(agg['mae'])[0]:.6f} / {_mstd(agg['mae'])[1]:.6f}\n")
+        f.write(f"MSE mean/std:  {_mstd(agg['mse'])[0]:.6f} / {_mstd(agg['mse'])[1]:.6f}\n")
+        f.write(f"PSNR mean/std: {_mstd(agg['psnr'])[0]:.3f} / {_mstd(agg['psnr'])[1]:.3f}\n")
+        f.write(f"SAM  mean/std: {_mstd(agg['sam'])[0]:.4f} / {_mstd(agg['sam'])[1]:.4f}\n")
+        f.write(f"ERGAS mean/std:{_mstd(agg['ergas'])[0]:.2f} / {_mstd(agg['ergas'])[1]:.2f}\n")
+    print("[DONE] DDIM (TRUE-INFER)")
+
+
+def cmd_onestep(args):
+    os.makedirs(args.out_dir, exist_ok=True)
+    device = torch.device("cuda")
+    files = _files(args)
+    x_cond, x_gt, mask, Cc, Ct = load_npz_as_tensors(os.path.join(args.patch_dir, files[0]), device)
+    model = load_model(args.ckpt, Cc + Ct, Ct, args.base_ch, device, 1)
+    _, _, alpha_bar = schedule.derive(schedule.cosine_beta_schedule(args.T))
+    alpha_bar = alpha_bar.to(device)
+    fn = samplers.one_step_recon_v if args.param == "v" else samplers.one_step_recon
+    if args.param == "v":       # the v script's t=0 identity check is real (Onestep_v_Prediction.py:184-197)
+        mae0, mse0, _ = fn(model, x_gt, x_cond, alpha_bar, mask, 0, noise=torch.zeros_like(x_gt))
+    else:                       # the eps script's is vacuous: x0_hat_t0 = x_t0 (Onestep.py:139)
+        mae0, mse0 = metrics.masked_mae(x_gt, x_gt, mask), metrics.masked_mse(x_gt, x_gt, mask)
+    print(f"[t=0 identity] MAE={mae0:.6f}  MSE={mse0:.6f}  (should be ~0.0)")
+    mae, mse, _ = fn(model, x_gt, x_cond, alpha_bar, mask, args.t_small)
+    print(f"[one-step@t={max(1, min(args.t_small, args.T - 1))}] MAE={mae:.6f}  MSE={mse:.6f}")
+
+
+def cmd_scene(args):
+    import torch.distributed as dist
+    from . import scene as sc
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if args.scene_npy:
+        scene = torch.from_numpy(np.load(args.scene_npy).astype(np.float32))
+    else:
+        scene = sc.synthetic_scene(args.scene_size, args.scene_size, seed=0)
+    model = load_model(args.ckpt, 8, 4, args.base_ch, device, args.batch) if args.ckpt else None
+    if model is None:
+        torch.manual_seed(1235)
+        model = UNetSmallB200(8, 4, args.base_ch, max_batch=args.batch).to(device).eval()
+    _, _, alpha_bar = schedule.derive(schedule.cosine_beta_schedule(args.T))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = sc.generate_scene(model, scene.to(device), alpha_bar, ps=args.patch_size, stride=args.stride, param=args.param,
+                            steps=args.ddim_steps, t_start=args.t_start, batch=args.batch, seed_base=args.seed_base,
+                            valid_ratio_threshold=args.valid_ratio_threshold, rank=rank, world=world)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        os.makedirs(args.out_dir, exist_ok=True)
+        np.save(os.path.join(args.out_dir, "scene_pred.npy"), res["canvas"].cpu().numpy())
+        np.save(os.path.join(args.out_dir, "scene_cover.npy"), res["cover"].cpu().numpy())
+        n = int(res["kept"].sum())
+        print(f"[DONE] scene {tuple(scene.shape)}: {n} patches on {world} GPU(s) in {dt:.2f} s = {n / dt:.2f} patches/s")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser("s1s2_b200 drivers")
+    ap.add_argument("cmd", choices=["onestep", "ddim", "ddim_v", "ddim_sweep", "true_infer", "scene"])
+    ap.add_argument("--patch_dir")
+    ap.add_argument("--ckpt")
+    ap.add_argument("--out_dir", required=True)
+    ap.add_argument("--T", type=int, default=1000)
+    ap.add_argument("--base_ch", type=int, default=96)
+    ap.add_argument("--max_files", type=int, default=0)
+    ap.add_argument("--t_start", type=int, default=200)
+    ap.add_argument("--ddim_steps", type=int, default=20)
+    ap.add_argument("--ddim_eta", type=float, default=0.0)
+    ap.add_argument("--t_small", type=int, default=20)
+    ap.add_argument("--n_seeds", type=int, default=8)
+    ap.add_argument("--seed_base", type=int, default=1234)
+    ap.add_argument("--t_start_grid", default="300,200,150,100")
+    ap.add_argument("--ddim_steps_grid", default="10,20,50,100")
+    ap.add_argument("--true_infer", action="store_true")
+    # additions
+    ap.add_argument("--param", default="eps", choices=["eps", "v"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--scene_npy", default=None, help="f32[4,H,W] scene (HH dB, HV dB, incidence deg, elevation m)")
+    ap.add_argument("--scene_size", type=int, default=2048)
+    ap.add_argument("--patch_size", type=int, default=256)
+    ap.add_argument("--stride", type=int, default=64)
+    ap.add_argument("--valid_ratio_threshold", type=float, default=0.0)
+    args = ap.parse_args(argv)
+    if args.cmd == "onestep":
+        cmd_onestep(args)
+    elif args.cmd == "ddim":
+        cmd_ddim(args, "eps")
+    elif args.cmd == "ddim_v":
+        cmd_ddim(args, "v")
+    elif args.cmd == "ddim_sweep":
+        cmd_sweep(args)
+    elif args.cmd == "true_infer":
+        cmd_true_infer(args)
+    else:
+        cmd_scene(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -310,3 +310,63 @@ def test_extract_sample_stitch_roundtrip(env):
     canvas, cover = patch.stitch(tiles, org, ps, st, H, W)
     assert bool(cover.all())
     assert float((canvas - truth).abs().max()) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ scene + drivers
+def test_scene_pipeline_single_rank(env):
+    """extract -> sample -> stitch composed by s1s2_b200.scene equals the pieces run by hand; stitch of the returned
+    patches is bit-exact against the oracle's numpy stitch."""
+    from s1s2_b200 import patch, scene as sc
+    scn = sc.synthetic_scene(96, 160, seed=5, nan_fraction=0.03)
+    scn[:, :40, :48] = float("nan")
+    ab = env["abar"]
+    res = sc.generate_scene(env["model"], scn.to(env["dev"]), ab, ps=32, stride=16, param="v", steps=3, batch=4,
+                            valid_ratio_threshold=0.5)
+    org = patch.tile_origins(96, 160, 32, 16)
+    assert np.array_equal(res["origins"], org)
+    vm = opatch.valid_mask(scn.numpy())
+    want_keep = np.array([vm[r:r + 32, c:c + 32].mean() >= 0.5 for r, c in org])
+    assert np.array_equal(res["kept"], want_keep) and 0 < want_keep.sum() < len(org)
+    ref_canvas, ref_cover = opatch.stitch(res["preds"].cpu().numpy(), org[want_keep], 96, 160)
+    assert np.array_equal(res["canvas"].cpu().numpy(), ref_canvas)
+    assert np.array_equal(res["cover"].cpu().numpy(), ref_cover)
+    # one patch by hand: same conditioning, same keyed noise, same sampler
+    k = int(np.nonzero(want_keep)[0][3])
+    cond, _, _ = patch.tile_extract(scn.to(env["dev"]), org[k:k + 1], 32)
+    z = sc.patch_noise([k], (4, 32, 32), 1234, env["dev"])
+    y = sc.sample_patches(env["model"], cond, ab, z, param="v", steps=3, batch=1)
+    assert torch.equal(y[0], res["preds"][3])
+
+
+def test_drivers_write_reference_outputs(env, tmp_path):
+    from s1s2_b200 import drivers
+    pdir, odir = tmp_path / "patches", tmp_path / "out"
+    pdir.mkdir()
+    rng = np.random.default_rng(0)
+    for i in range(5):
+        np.savez_compressed(pdir / f"patch_{i:06d}.npz", inputs=rng.normal(size=(4, 32, 32)).astype(np.float32),
+                            target=rng.random((4, 32, 32)).astype(np.float32), mask=(rng.random((32, 32)) > 0.1).astype(np.uint8))
+    ckpt = tmp_path / "ddpm_s1_to_s2_v3.pth"
+    torch.save({"model": env["sd"]}, ckpt)                    # wrapped form (DDIM_Multi-step_v_Prediction.py:264-270)
+    common = ["--patch_dir", str(pdir), "--ckpt", str(ckpt), "--batch", "2"]
+    drivers.main(["ddim", "--out_dir", str(odir / "a"), "--t_start", "200", "--ddim_steps", "3"] + common)
+    rows = list(__import__("csv").reader(open(odir / "a" / "ddim_metrics.csv")))
+    assert rows[0] == ["file", "t_start", "ddim_steps", "MAE", "MSE"] and len(rows) == 6
+    assert open(odir / "a" / "ddim_summary.txt").read().startswith("files: 5  t_start: 200  steps: 3\n")
+    drivers.main(["ddim_v", "--out_dir", str(odir / "b"), "--t_start", "999", "--ddim_steps", "3"] + common)
+    assert list(__import__("csv").reader(open(odir / "b" / "ddim_metrics.csv")))[0][3] == "eta"
+    drivers.main(["ddim_sweep", "--out_dir", str(odir / "c"), "--t_start_grid", "200,100", "--ddim_steps_grid", "2,3"] + common)
+    rows = list(__import__("csv").reader(open(odir / "c" / "ddim_sweep_summary.csv")))
+    assert rows[0][:7] == ["t_start", "steps", "files", "MAE_mean", "MAE_std", "MSE_mean", "MSE_std"] and len(rows) == 5
+    drivers.main(["true_infer", "--out_dir", str(odir / "d"), "--t_start", "999", "--ddim_steps", "3", "--n_seeds", "2"] + common)
+    rows = list(__import__("csv").reader(open(odir / "d" / "ddim_true_infer_metrics.csv")))
+    assert rows[0][-3:] == ["PSNR_mean", "SAM_mean", "ERGAS_mean"] and len(rows) == 6
+    drivers.main(["onestep", "--out_dir", str(odir / "e"), "--t_small", "20"] + common)
+    # per-patch results do not depend on the batch size
+    drivers.main(["ddim_sweep", "--out_dir", str(odir / "f"), "--t_start_grid", "200", "--ddim_steps_grid", "3",
+                  "--patch_dir", str(pdir), "--ckpt", str(ckpt), "--batch", "1"])
+    drivers.main(["ddim_sweep", "--out_dir", str(odir / "g"), "--t_start_grid", "200", "--ddim_steps_grid", "3",
+                  "--patch_dir", str(pdir), "--ckpt", str(ckpt), "--batch", "4"])
+    a = list(__import__("csv").reader(open(odir / "f" / "ddim_sweep_summary.csv")))[1][:7]
+    b = list(__import__("csv").reader(open(odir / "g" / "ddim_sweep_summary.csv")))[1][:7]
+    assert a == b
