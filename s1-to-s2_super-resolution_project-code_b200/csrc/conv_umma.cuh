@@ -87,16 +87,16 @@ struct ConvParams {
     HeadParams head;              // MODE_HEAD only
 };
 
-template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE>
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS>
 struct ConvSmem {
     static constexpr int kABox = 128 * KBOX * 2;
-    static constexpr int kBBox = (BLOCK_N / 2) * KBOX * 2;      // this CTA's half of the weight rows
+    static constexpr int kBBox = (BLOCK_N / CTAS) * KBOX * 2;   // this CTA's share of the weight rows
     static constexpr int kStage = BOXES * (kABox + kBBox);
     // output staging for the TMA store: one [rows][32 channels] fp16 sub-tile (64-byte rows, 64B swizzle) per
     // 32-column accumulator chunk; rows = 128 pixels, or the 32 pooled pixels of the tile
     static constexpr int kSubRows = MODE == MODE_POOL ? 32 : 128;
     static constexpr int kSubBytes = kSubRows * 64;
-    static constexpr int kStaging = (MODE == MODE_STORE || MODE == MODE_POOL) ? (BLOCK_N / 32) * kSubBytes : 0;
+    static constexpr int kStaging = (MODE != MODE_HEAD) ? (BLOCK_N / 32) * kSubBytes : 0;
     static constexpr int kBias = 1536 * 4;
     static constexpr int kBytes = 1024 /*align slack*/ + STAGES * kStage + kStaging + kBias + 256 /*barriers*/;
     static_assert(kStage % 512 == 0, "stage alignment");
@@ -127,16 +127,19 @@ __device__ __forceinline__ float range_scale(uint32_t amax_bits, float& s) {
     return __uint_as_float(static_cast<uint32_t>(127 - k) << 23);
 }
 
-template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+// CTAS = 2: CTA pair (cta_group::2, M = 256 per MMA, weight rows split across the pair).  CTAS = 1: single-CTA MMAs
+// (M = 128), kept for A/B measurements of the pairing itself.
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS>
+__global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(256, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
-    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE>;
-    constexpr bool kTmaStore = (MODE == MODE_STORE || MODE == MODE_POOL);
+    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE, CTAS>;
+    constexpr bool kPair = CTAS == 2;
+    constexpr bool kTmaStore = (MODE != MODE_HEAD);
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
     static_assert(KBOX == 16 || KBOX == 32 || KBOX == 64, "KBOX");
     constexpr int kRowBytes = KBOX * 2;
     constexpr int kAccStride = 256;            // TMEM columns between the two accumulators
-    constexpr uint32_t kIdesc = umma_idesc_f16(256, BLOCK_N);
+    constexpr uint32_t kIdesc = umma_idesc_f16(128 * CTAS, BLOCK_N);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -152,11 +155,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int cluster_id = blockIdx.x >> 1;
-    const int num_clusters = gridDim.x >> 1;
-    const int m_pairs = (p.num_m_tiles + 1) >> 1;
-    const int num_tiles = m_pairs * p.num_n_tiles;          // pair tiles: 2 M tiles x 1 N tile
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / CTAS;
+    const int num_clusters = gridDim.x / CTAS;
+    const int m_pairs = (p.num_m_tiles + CTAS - 1) / CTAS;
+    const int num_tiles = m_pairs * p.num_n_tiles;          // group tiles: CTAS M tiles x 1 N tile
     const int k_iters = (p.taps_w * p.taps_w * p.chunks) / BOXES;
     const int pad = p.taps_w >> 1;
 
@@ -172,18 +175,18 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);        // one multicast commit
-            mbar_init(&tempty_bar[a], 8);       // one arrive per epilogue warp of both CTAs
+            mbar_init(&tempty_bar[a], 4 * CTAS); // one arrive per epilogue warp of every CTA of the group
         }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
+    if (warp == 2) { if constexpr (kPair) tmem_alloc_pair<512>(tmem_slot); else tmem_alloc<512>(tmem_slot); }
     {   // bias for every N tile of this layer, staged once
         const int nb = p.num_n_tiles * BLOCK_N;
         for (int i = threadIdx.x; i < nb; i += blockDim.x) sbias[i] = p.bias[i];
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                         // peer's barriers are initialised before anything targets them
+    if constexpr (kPair) cluster_sync_all();    // peer's barriers are initialised before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -198,14 +201,14 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         int issued = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int n_tile = tile % p.num_n_tiles;
-            const int m_tile = 2 * (tile / p.num_n_tiles) + static_cast<int>(rank);
+            const int m_tile = CTAS * (tile / p.num_n_tiles) + static_cast<int>(rank);
             const int tx = m_tile % p.tiles_x;
             const int ty = (m_tile / p.tiles_x) % p.tiles_y;
             const int tn = m_tile / (p.tiles_x * p.tiles_y);
             const int x0 = (tx << p.tw_log2) - pad;
             const int y0 = (ty << p.th_log2) - pad;
             const int n0 = tn << (7 - p.tw_log2 - p.th_log2);    // past the batch for a phantom tile: zero fill
-            const int b_row0 = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+            const int b_row0 = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
             int chunk = 0, kx = 0, ky = 0, kcol = 0;             // running (tap, chunk) position, no divisions
             for (int it = 0; it < k_iters; ++it, ++issued) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
@@ -213,18 +216,18 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 const bool load_b = !((p.perf_mode & 2) && issued >= STAGES);
                 uint8_t* a_dst = stage_base + s * L::kStage;
                 uint8_t* b_dst = a_dst + BOXES * L::kABox;
-                const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[s]), 0);
+                const uint32_t full_leader = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
                 if (elect_one()) {
                     if (rank == 0)
-                        mbar_expect_tx(&full_bar[s], 2 * BOXES * ((load_a ? L::kABox : 0) + (load_b ? L::kBBox : 0)));
+                        mbar_expect_tx(&full_bar[s], CTAS * BOXES * ((load_a ? L::kABox : 0) + (load_b ? L::kBBox : 0)));
 #pragma unroll
                     for (int b = 0; b < BOXES; ++b) {
                         int c_ = chunk + b, kx_ = kx, ky_ = ky;                  // BOXES <= chunks or chunks == 1
                         if (p.chunks == 1) { kx_ += b; if (kx_ >= p.taps_w) { kx_ -= p.taps_w; ++ky_; } c_ = 0; }
                         if (load_a)
-                            tma_load_4d_pair(a_dst + b * L::kABox, &p.tmap_a, full_leader, c_ * KBOX, x0 + kx_, y0 + ky_, n0);
+                            tma_load_4d_g<kPair>(a_dst + b * L::kABox, &p.tmap_a, full_leader, c_ * KBOX, x0 + kx_, y0 + ky_, n0);
                         if (load_b)
-                            tma_load_2d_pair(b_dst + b * L::kBBox, &p.tmap_b, full_leader, kcol + b * KBOX, b_row0);
+                            tma_load_2d_g<kPair>(b_dst + b * L::kBBox, &p.tmap_b, full_leader, kcol + b * KBOX, b_row0);
                     }
                 }
                 __syncwarp();
@@ -264,11 +267,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
                             for (int k = 0; k < KBOX / 16; ++k) {
                                 // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
-                                umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (it | b | k) != 0 ? 1u : 0u);
+                                umma_f16_g<kPair>(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (it | b | k) != 0 ? 1u : 0u);
                             }
                         }
-                        umma_commit_pair(&empty_bar[s]);        // both CTAs' slots reusable once these MMAs retire
-                        if (it == k_iters - 1) umma_commit_pair(&tfull_bar[acc]);
+                        umma_commit_g<kPair>(&empty_bar[s]);    // (both CTAs') slots reusable once these MMAs retire
+                        if (it == k_iters - 1) umma_commit_g<kPair>(&tfull_bar[acc]);
                     }
                     __syncwarp();
                     if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -289,7 +292,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         uint32_t acc_ph = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int n_tile = tile % p.num_n_tiles;
-            const int m_tile = 2 * (tile / p.num_n_tiles) + static_cast<int>(rank);
+            const int m_tile = CTAS * (tile / p.num_n_tiles) + static_cast<int>(rank);
             const int tx = m_tile % p.tiles_x;
             const int ty = (m_tile / p.tiles_x) % p.tiles_y;
             const int tn = m_tile / (p.tiles_x * p.tiles_y);
@@ -304,7 +307,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
             const float* bias_t = sbias + n_tile * BLOCK_N;
-            const uint32_t tempty_leader = mapa_shared(smem_u32(&tempty_bar[acc]), 0);
+            const uint32_t tempty_leader = kPair ? mapa_shared(smem_u32(&tempty_bar[acc]), 0) : smem_u32(&tempty_bar[acc]);
 
             if constexpr (MODE == MODE_HEAD) {
                 static_assert(MODE != MODE_HEAD || BLOCK_N == kHeadIn, "head wants all channels of a pixel");
@@ -388,16 +391,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     }
                 }
             } else {
-                // STORE / POOL: the tile is staged in shared memory ([row][32 ch] sub-tiles, 64B swizzle) and leaves
-                // through TMA stores (full-sector, asynchronous, clipped at the image / batch border).
-                // CONVT: direct stores to the (2y+ky, 2x+kx) pixels of the tap this 32-column chunk belongs to.
+                // The tile is staged in shared memory ([row][32 ch] sub-tiles, 64B swizzle) and leaves through TMA
+                // stores (full-sector, asynchronous, clipped at the image / batch border).  CONVT: the 32 columns of a
+                // sub-tile belong to one tap (ky, kx); its store walks the output with element strides (1, 2, 2, 1)
+                // from (co, 2*x0 + kx, 2*y0 + ky), i.e. the pixel shuffle is done by the TMA unit.
                 int srow = m;                                  // staging row of this thread's pixel
                 bool writer = true;
                 if constexpr (MODE == MODE_POOL) {
                     writer = ((lx | ly) & 1) == 0;
                     srow = ((ln << (p.th_log2 - 1)) + (ly >> 1)) * (tw >> 1) + (lx >> 1);
-                } else if constexpr (MODE == MODE_CONVT) {
-                    writer = live;
                 }
                 if constexpr (kTmaStore) {
                     if (warp == 4 && lane == 0) bulk_wait_read0();      // previous tile's stores have read the staging
@@ -436,19 +438,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                             *reinterpret_cast<uint4*>(row + ((2 ^ sw) << 4)) = make_uint4(h[8], h[9], h[10], h[11]);
                             *reinterpret_cast<uint4*>(row + ((3 ^ sw) << 4)) = make_uint4(h[12], h[13], h[14], h[15]);
                         }
-                    } else {
-                        const int ng = n_tile * BLOCK_N + c * 32;
-                        const int tap = ng / p.cout;
-                        const int co = ng - tap * p.cout;
-                        const int oy = 2 * y + (tap >> 1), ox = 2 * x + (tap & 1);
-                        __half* dst = p.out + ((static_cast<size_t>(n) * (2 * p.H) + oy) * (2 * p.W) + ox) * p.out_cpitch + co;
-                        if (writer) {
-                            uint4* d4 = reinterpret_cast<uint4*>(dst);
-                            d4[0] = make_uint4(h[0], h[1], h[2], h[3]);
-                            d4[1] = make_uint4(h[4], h[5], h[6], h[7]);
-                            d4[2] = make_uint4(h[8], h[9], h[10], h[11]);
-                            d4[3] = make_uint4(h[12], h[13], h[14], h[15]);
-                        }
                     }
                 }
                 tc_fence_before();
@@ -458,12 +447,23 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     fence_proxy_async_smem();
                     named_bar_sync(1, 128);
                     if (warp == 4 && lane == 0) {
-                        const int sh = MODE == MODE_POOL ? 1 : 0;
-                        const int ox0 = (tx << p.tw_log2) >> sh, oy0 = (ty << p.th_log2) >> sh;
                         const int on0 = tn << (7 - p.tw_log2 - p.th_log2);
+                        if constexpr (MODE == MODE_CONVT) {
+                            const int ox0 = 2 * (tx << p.tw_log2), oy0 = 2 * (ty << p.th_log2);
 #pragma unroll
-                        for (int c = 0; c < BLOCK_N / 32; ++c)
-                            tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, n_tile * BLOCK_N + c * 32, ox0, oy0, on0);
+                            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                                const int ng = n_tile * BLOCK_N + c * 32;
+                                const int tap = ng / p.cout;
+                                tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, ng - tap * p.cout, ox0 + (tap & 1),
+                                             oy0 + (tap >> 1), on0);
+                            }
+                        } else {
+                            const int sh = MODE == MODE_POOL ? 1 : 0;
+                            const int ox0 = (tx << p.tw_log2) >> sh, oy0 = (ty << p.th_log2) >> sh;
+#pragma unroll
+                            for (int c = 0; c < BLOCK_N / 32; ++c)
+                                tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, n_tile * BLOCK_N + c * 32, ox0, oy0, on0);
+                        }
                         bulk_commit();
                     }
                 }
@@ -478,10 +478,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                         // both CTAs are done with each other's shared memory and TMEM
+    if constexpr (kPair) cluster_sync_all();    // both CTAs are done with each other's shared memory and TMEM
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc_pair<512>(tmem_base);
+        if constexpr (kPair) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
     }
 }
 

@@ -206,6 +206,36 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
         : "memory");
 }
 
+// Pair / single dispatch used by the conv kernel (barrier addresses are shared::cluster-valid 32-bit addresses).
+template <bool kPair>
+__device__ __forceinline__ void tma_load_2d_g(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    if constexpr (kPair) tma_load_2d_pair(dst, m, bar, c0, c1);
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+            : "memory");
+}
+template <bool kPair>
+__device__ __forceinline__ void tma_load_4d_g(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+    if constexpr (kPair) tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+            : "memory");
+}
+template <bool kPair>
+__device__ __forceinline__ void umma_f16_g(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if constexpr (kPair) umma_f16_pair(tmem_d, adesc, bdesc, idesc, acc);
+    else umma_f16(tmem_d, adesc, bdesc, idesc, acc);
+}
+template <bool kPair>
+__device__ __forceinline__ void umma_commit_g(uint64_t* bar) {
+    if constexpr (kPair) umma_commit_pair(bar);
+    else umma_commit(bar);
+}
+
 // 32 lanes x 32 columns of fp32: thread i of the warp receives columns [c, c+32) of TMEM lane (lane_base + i).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(

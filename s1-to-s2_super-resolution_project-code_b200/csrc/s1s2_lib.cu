@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -164,21 +165,22 @@ CUtensorMapSwizzle swizzle_for(int kbox) {
 }
 
 // ---------------------------------------------------------------------------------------------- layers
-enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_COUNT };
+enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_STORE256_1, K_POOL256_1, K_COUNT };
 
 struct KernelInfo {
     void (*fn)(const ConvParams);
-    int block_n, kbox, boxes, smem, mode;
+    int block_n, kbox, boxes, smem, mode, ctas;
 };
 
-template <int BN, int KB, int BX, int ST, int MODE>
+template <int BN, int KB, int BX, int ST, int MODE, int CTAS = 2>
 KernelInfo make_kernel() {
     KernelInfo k;
-    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE>;
+    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS>;
+    k.ctas = CTAS;
     k.block_n = BN;
     k.kbox = KB;
     k.boxes = BX;
-    k.smem = ConvSmem<BN, KB, BX, ST, MODE>::kBytes;
+    k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS>::kBytes;
     k.mode = MODE;
     return k;
 }
@@ -193,11 +195,13 @@ const KernelInfo* kernel_table() {
         t[K_C96IN] = make_kernel<192, 32, 3, 4, MODE_STORE>();  // Cin = 96 (64-byte swizzle rows)
         t[K_STORE] = make_kernel<192, 64, 1, 6, MODE_STORE>();
         t[K_POOL] = make_kernel<192, 64, 1, 7, MODE_POOL>();
-        t[K_CONVT] = make_kernel<192, 64, 1, 7, MODE_CONVT>();
+        t[K_CONVT] = make_kernel<192, 64, 1, 6, MODE_CONVT>();
         t[K_STORE256] = make_kernel<256, 64, 1, 4, MODE_STORE>();
         t[K_POOL256] = make_kernel<256, 64, 1, 6, MODE_POOL>();
-        t[K_CONVT256] = make_kernel<256, 64, 1, 6, MODE_CONVT>();
+        t[K_CONVT256] = make_kernel<256, 64, 1, 4, MODE_CONVT>();
         t[K_N96] = make_kernel<96, 64, 1, 8, MODE_STORE>();     // Cout = 96
+        t[K_STORE256_1] = make_kernel<256, 64, 1, 3, MODE_STORE, 1>();   // single-CTA variants: A/B measurement only
+        t[K_POOL256_1] = make_kernel<256, 64, 1, 4, MODE_POOL, 1>();     // (S1S2_SINGLE_CTA_256=1)
         t[K_HEAD] = make_kernel<96, 32, 3, 6, MODE_HEAD>();     // conv1.2 + outc + scheduler
         init = true;
     }
@@ -316,7 +320,7 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
         const int ktot = L.taps_w * L.taps_w * L.cin;
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(L.ntot)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
-        cuuint32_t box[2] = {static_cast<cuuint32_t>(k.kbox), static_cast<cuuint32_t>(k.block_n / 2)};   // per CTA of the pair
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(k.kbox), static_cast<cuuint32_t>(k.block_n / k.ctas)};   // per CTA of the group
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&p.tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L.w, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(k.kbox), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -326,20 +330,23 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
             return S1S2_ERR_CUDA;
         }
     }
-    if (k.mode == MODE_STORE || k.mode == MODE_POOL) {
-        // destination: (C, W, H, N) of the (pooled) output, box = 32 channels x the (pooled) pixel tile, 64B swizzle
+    if (k.mode != MODE_HEAD) {
+        // destination: (C, W, H, N) of the output, box = 32 channels x the output pixels of one M tile, 64B swizzle.
+        //   STORE: same resolution.  POOL: half resolution, box = the pooled tile.  CONVT: double resolution walked
+        //   with element strides (1, 2, 2, 1): one tap's pixels (2x+kx, 2y+ky) of the tile per store.
         const int sh = k.mode == MODE_POOL ? 1 : 0;
+        const int up = k.mode == MODE_CONVT ? 2 : 1;
         if (sh && (g.tw_log2 < 1 || g.th_log2 < 1)) {
             set_err(err, "layer %s: pooled tile needs an M tile at least 2 x 2 pixels", L.name);
             return S1S2_ERR_INVALID;
         }
-        const int Ho = Hl >> sh, Wo = Wl >> sh;
-        cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.ntot), static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Ho),
+        const int Ho = (Hl >> sh) * up, Wo = (Wl >> sh) * up;
+        cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cout), static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Ho),
                               static_cast<cuuint64_t>(h->nalloc)};
         cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.dst_pitch) * 2, static_cast<cuuint64_t>(Wo) * L.dst_pitch * 2,
                                  static_cast<cuuint64_t>(Ho) * Wo * L.dst_pitch * 2};
-        cuuint32_t box[4] = {32u, (1u << g.tw_log2) >> sh, (1u << g.th_log2) >> sh, static_cast<cuuint32_t>(g.tn)};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
+        cuuint32_t box[4] = {32u, ((1u << g.tw_log2) >> sh) * up, ((1u << g.th_log2) >> sh) * up, static_cast<cuuint32_t>(g.tn)};
+        cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(up), static_cast<cuuint32_t>(up), 1};
         CUresult r = enc(&p.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, L.dst, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -374,9 +381,9 @@ int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, cudaS
     p.B = B;
     p.num_m_tiles = p.tiles_x * p.tiles_y * ((B + tn - 1) / tn);
     p.amax_in = amax_in;
-    const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;      // one CTA pair per (2 M tiles, 1 N tile)
-    const int clusters = pair_tiles < h->num_sms / 2 ? pair_tiles : h->num_sms / 2;
-    k.fn<<<2 * clusters, 256, k.smem, st>>>(p);                            // __cluster_dims__(2, 1, 1)
+    const int group_tiles = ((p.num_m_tiles + k.ctas - 1) / k.ctas) * p.num_n_tiles;   // one CTA group per (ctas M tiles, 1 N tile)
+    const int clusters = group_tiles < h->num_sms / k.ctas ? group_tiles : h->num_sms / k.ctas;
+    k.fn<<<k.ctas * clusters, 256, k.smem, st>>>(p);                       // __cluster_dims__(ctas, 1, 1)
     CK(cudaGetLastError());
     ++h->launches;
     return S1S2_OK;
@@ -531,6 +538,12 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     add("conv1.0",     K_N96,    0,  192, 96,   96,  3,   cat1,        192,  c1a,          96);
     add("conv1.2",     K_HEAD,   0,  96,  96,   96,  3,   c1a,         96,   nullptr,      0);
 
+    if (getenv("S1S2_SINGLE_CTA_256") != nullptr) {
+        for (Layer& L : h->layers) {
+            if (L.kid == K_STORE256) L.kid = K_STORE256_1;
+            if (L.kid == K_POOL256) L.kid = K_POOL256_1;
+        }
+    }
     for (Layer& L : h->layers) {
         const size_t welems = static_cast<size_t>(L.ntot) * L.taps_w * L.taps_w * L.cin;
         void* p;
