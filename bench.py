@@ -225,9 +225,9 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import __graft_entry__ as ge
+    from s1s2_b200 import _build
     if rank == 0:
-        ge.build()
+        _build.build()                              # no-op when the in-tree .so is current (stdout stays one JSON line)
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product path has no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -1,0 +1,296 @@
+// Pixels-on-N convolution kernel for the narrow (Cout = 96) full-resolution layers: conv1.0 and conv1.2 (+ outc + scheduler).
+//
+// The measured cost of one tcgen05.mma is ~128 cycles per 128 M rows for ANY N <= 256 (profiles/r1_attribution_loops.txt),
+// so conv_umma_kernel, which puts Cout on N, runs a Cout = 96 layer at 96/256 = 37.5 % of the tensor pipe.  Here the
+// GEMM is transposed:
+//
+//   D^T[cout, pixel] = sum_{tap, cin} Wt[cout, tap, cin] * X[pixel shifted by tap, cin]
+//
+// M = 128 weight rows (96 real; the TMA box overhangs the 96-row weight tensor and the overhang is zero-filled), N = 256
+// pixels = one 16 x 16 spatial tile of one image, K chunks of KBOX channels per tap.  Same TMA boxes, swizzles and UMMA
+// descriptors as conv_umma_kernel with the operand roles swapped; single CTA (cta_group::1).
+//
+// Epilogue: a thread owns one output channel (TMEM lane) and sees the tile's 256 pixels as columns.  bias + ReLU in
+// fp32, then the tile is transposed through shared memory, half a tile (8 image rows) at a time to keep the staging at
+// 24 KB and the operand ring deep, into the [pixel][32 ch] 64B-swizzled sub-tiles that
+//   * MODE_STORE: TMA stores write to the NHWC destination (conv1.0);
+//   * MODE_HEAD:  a second pass reads back pixel-major - one thread per pixel - to apply the 1x1 outc (96 -> 4, fp32
+//                 accumulation over the fp16 hidden row), the scheduler update, and the writes of x_{t-1}, the next
+//                 input record, the eps/v tap and max|x_{t-1}| (same arithmetic as conv_umma_kernel's MODE_HEAD).
+#pragma once
+#include "conv_umma.cuh"
+
+namespace s1s2 {
+
+template <int KBOX, int STAGES>
+struct PxSmem {
+    static constexpr int kABox = 128 * KBOX * 2;        // weights: 128 rows (cout, zero-padded past the real rows)
+    static constexpr int kBBox = 256 * KBOX * 2;        // pixels: 16 x 16 tile
+    static constexpr int kStage = kABox + kBBox;
+    static constexpr int kSubBytes = 128 * 64;          // [128 pixels = half a tile][32 ch] fp16, 64B swizzle
+    static constexpr int kStaging = 3 * kSubBytes;
+    static constexpr int kBias = 128 * 4;
+    static constexpr int kBytes = 1024 + STAGES * kStage + kStaging + kBias + 256;
+    static_assert(kBytes <= 232448, "shared memory budget");
+};
+
+template <int KBOX, int STAGES, int MODE>
+__global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__ ConvParams p) {
+    using L = PxSmem<KBOX, STAGES>;
+    static_assert(MODE == MODE_STORE || MODE == MODE_HEAD, "conv_px_kernel modes");
+    constexpr int kRowBytes = KBOX * 2;
+    constexpr int kAccStride = 256;
+    constexpr uint32_t kIdesc = umma_idesc_f16(128, 256);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint8_t* sout = smem + STAGES * L::kStage;
+    float* sbias = reinterpret_cast<float*>(sout + L::kStaging);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sout + L::kStaging + L::kBias);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tfull_bar = bars + 2 * STAGES;
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_x = p.W >> 4, tiles_y = p.H >> 4;
+    const int num_tiles = tiles_x * tiles_y * p.B;
+    const int k_iters = 9 * p.chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmap_a);
+        tma_prefetch_desc(&p.tmap_b);
+        if constexpr (MODE == MODE_STORE) tma_prefetch_desc(&p.tmap_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    if (threadIdx.x < 128) sbias[threadIdx.x] = threadIdx.x < p.cout ? p.bias[threadIdx.x] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tx = tile % tiles_x;
+            const int ty = (tile / tiles_x) % tiles_y;
+            const int n = tile / (tiles_x * tiles_y);
+            const int x0 = (tx << 4) - 1, y0 = (ty << 4) - 1;
+            int chunk = 0, kx = 0, ky = 0, kcol = 0;
+            for (int it = 0; it < k_iters; ++it) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* a_dst = stage_base + s * L::kStage;
+                if (elect_one()) {
+                    mbar_expect_tx(&full_bar[s], L::kStage);
+                    tma_load_2d(a_dst, &p.tmap_b, &full_bar[s], kcol, 0);                                   // weights
+                    tma_load_4d(a_dst + L::kABox, &p.tmap_a, &full_bar[s], chunk * KBOX, x0 + kx, y0 + ky, n);  // pixels
+                }
+                __syncwarp();
+                if (++chunk == p.chunks) {
+                    chunk = 0;
+                    kcol += p.tap_kstride - (p.chunks - 1) * KBOX;      // first K column of the next tap
+                    if (++kx == 3) { kx = 0; ++ky; }
+                } else {
+                    kcol += KBOX;
+                }
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        int s = 0;
+        uint32_t ph = 0;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        const uint32_t stage0 = smem_u32(stage_base);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * kAccStride;
+            for (int it = 0; it < k_iters; ++it) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t w_addr = stage0 + s * L::kStage;
+                if (elect_one()) {
+                    const uint64_t adesc = umma_smem_desc<kRowBytes>(w_addr);                 // M side: weights
+                    const uint64_t bdesc = umma_smem_desc<kRowBytes>(w_addr + L::kABox);      // N side: pixels
+#pragma unroll
+                    for (int k = 0; k < KBOX / 16; ++k)
+                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (it | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                    if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_ph ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ================================================================= epilogue
+        const int q = warp & 3;                     // TMEM lane quadrant = 32 output channels
+        const int et = q * 32 + lane;               // epilogue thread index 0..127 (= output channel in pass 1)
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tx = tile % tiles_x;
+            const int ty = (tile / tiles_x) % tiles_y;
+            const int n = tile / (tiles_x * tiles_y);
+            float s_up = 1.f, s_dn = 1.f;
+            if (p.amax_in != nullptr) s_dn = range_scale(__ldg(p.amax_in + n), s_up);
+
+            mbar_wait(&tfull_bar[acc], acc_ph);
+            tc_fence_after();
+            const StepCoef& sc = p.head.step;
+            const size_t plane = static_cast<size_t>(p.H) * p.W;
+            float amax = 0.f;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                if constexpr (MODE == MODE_STORE) {
+                    if (warp == 4 && lane == 0) bulk_wait_read0();   // the previous stores have read the staging
+                }
+                named_bar_sync(1, 128);                              // (HEAD: the previous pass 2 is done)
+                if (q < 3) {
+                    // pass 1: this thread's channel, 128 pixels of the half tile -> staging[pixel][channel]
+                    const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
+                    const float b = sbias[et] * s_dn;
+                    uint8_t* sub = sout + q * L::kSubBytes + (lane & 7) * 2;
+                    const int cchunk = lane >> 3;                    // 16-byte chunk of this channel inside a 64-byte row
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr + j * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int px = j * 32 + i;
+                            const float v = fminf(fmaxf(__uint_as_float(r[i]) + b, 0.f), 65504.f);
+                            *reinterpret_cast<__half*>(sub + px * 64 + ((cchunk ^ ((px >> 1) & 3)) << 4)) = __float2half_rn(v);
+                        }
+                    }
+                }
+                if (half == 1) {                                     // accumulator drained: MMAs of tile+2 may start
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                }
+                if constexpr (MODE == MODE_STORE) {
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (warp == 4 && lane == 0) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, c * 32, tx << 4, (ty << 4) + half * 8, n);
+                        bulk_commit();
+                    }
+                } else {
+                    named_bar_sync(1, 128);                          // hidden half tile complete in shared memory
+                    // pass 2: this thread's pixel: outc over the 96 hidden channels, scheduler update, writes
+                    const int px = et;
+                    const int x = (tx << 4) + (px & 15), y = (ty << 4) + half * 8 + (px >> 4);
+                    float o[kHeadOut];
+#pragma unroll
+                    for (int k = 0; k < kHeadOut; ++k) o[k] = p.head.b[k] * s_dn;
+                    const int sw = (px >> 1) & 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(sout + c * L::kSubBytes + px * 64 + ((g ^ sw) << 4));
+                            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 hh = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+                                const int ch = c * 32 + g * 8 + e * 2;
+#pragma unroll
+                                for (int k = 0; k < kHeadOut; ++k) {
+                                    o[k] = fmaf(hh.x, p.head.w[k * kHeadIn + ch], o[k]);
+                                    o[k] = fmaf(hh.y, p.head.w[k * kHeadIn + ch + 1], o[k]);
+                                }
+                            }
+                        }
+                    }
+                    const size_t pix = static_cast<size_t>(y) * p.W + x;
+                    float res[kHeadOut];
+#pragma unroll
+                    for (int k = 0; k < kHeadOut; ++k) {
+                        const size_t idx = (static_cast<size_t>(n) * kHeadOut + k) * plane + pix;
+                        const float pr = o[k] * s_up;
+                        if (p.head.pred_out != nullptr) p.head.pred_out[idx] = pr;
+                        res[k] = pr;
+                        if (sc.kind != STEP_NONE) {
+                            const float xt = p.head.x_t[idx];
+                            float x0 = 0.f, e = pr, xn;
+                            if (sc.kind == STEP_EPS_DDIM) {
+                                x0 = __fdiv_rn(__fsub_rn(xt, __fmul_rn(sc.c0, pr)), sc.c1);
+                            } else if (sc.kind == STEP_V_DDIM || sc.kind == STEP_V_DDPM) {
+                                x0 = __fsub_rn(__fmul_rn(sc.c0, xt), __fmul_rn(sc.c1, pr));
+                                e = __fadd_rn(__fmul_rn(sc.c1, xt), __fmul_rn(sc.c0, pr));
+                            }
+                            const bool ddpm = sc.kind == STEP_EPS_DDPM || sc.kind == STEP_V_DDPM;
+                            if (ddpm) xn = __fmul_rn(sc.c2, __fsub_rn(xt, __fmul_rn(sc.c3, e)));
+                            else      xn = __fadd_rn(__fmul_rn(sc.c2, x0), __fmul_rn(sc.c3, e));
+                            if (sc.flags & STEP_FLAG_NOISE) xn = __fadd_rn(xn, __fmul_rn(sc.c4, p.head.noise[idx]));
+                            if (sc.flags & STEP_FLAG_FINAL) xn = fminf(fmaxf(ddpm ? xn : x0, 0.f), 1.f);
+                            p.head.x_t[idx] = xn;
+                            res[k] = xn;
+                            amax = fmaxf(amax, fabsf(xn));
+                        }
+                    }
+                    if (sc.kind != STEP_NONE && p.head.xin16 != nullptr) {
+                        float hi[kHeadOut], lo[kHeadOut];
+#pragma unroll
+                        for (int k = 0; k < kHeadOut; ++k) split_x(res[k], hi[k], lo[k]);
+                        __half* rec = p.head.xin16 + ((static_cast<size_t>(n) * p.H + y) * p.W + x) * 16;
+                        uint4 v;
+                        v.x = pack_half2_sat(lo[0], lo[1]);
+                        v.y = pack_half2_sat(lo[2], lo[3]);
+                        v.z = pack_half2_sat(sc.t_next, sc.t_next);
+                        v.w = 0u;
+                        *reinterpret_cast<uint4*>(rec) = v;
+                        uint2 u;
+                        u.x = pack_half2_sat(hi[0], hi[1]);
+                        u.y = pack_half2_sat(hi[2], hi[3]);
+                        *reinterpret_cast<uint2*>(rec + 12) = u;
+                    }
+                }
+            }
+            if constexpr (MODE == MODE_HEAD) {
+                if (sc.kind != STEP_NONE && p.head.amax_out != nullptr) {
+                    const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));   // one image per tile
+                    if (lane == 0) atomicMax(p.head.amax_out + n, mx);
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_ph ^= 1;
+        }
+        if constexpr (MODE == MODE_STORE) {
+            if (warp == 4 && lane == 0) bulk_wait0();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace s1s2

@@ -80,6 +80,7 @@ struct ConvParams {
     int num_m_tiles, num_n_tiles;
     int taps_w;                   // 3 -> 3x3 pad 1 ; 1 -> 1x1 / transposed-conv GEMM
     int chunks;                   // K chunks of KBOX channels per tap
+    int tap_kstride;              // conv_px_kernel: K columns between consecutive taps in the weight rows (= Cin)
     int cout;                     // real channels per output pixel (CONVT: per tap)
     int flags;                    // LAYER_FLAG_*
     int perf_mode;                // measurement aid (s1s2_debug_loop_layer): bit 0 / bit 1 = stop re-loading A / B

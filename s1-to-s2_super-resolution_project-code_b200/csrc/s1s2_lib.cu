@@ -21,6 +21,7 @@
 
 #include "../../include/s1s2_b200.h"
 #include "conv_umma.cuh"
+#include "conv_px.cuh"
 #include "patch_kernels.cuh"
 
 using namespace s1s2;
@@ -165,11 +166,12 @@ CUtensorMapSwizzle swizzle_for(int kbox) {
 }
 
 // ---------------------------------------------------------------------------------------------- layers
-enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_STORE256_1, K_POOL256_1, K_COUNT };
+enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_STORE256_1, K_POOL256_1, K_PX_STORE, K_PX_HEAD, K_PX_HEAD32, K_COUNT };
 
 struct KernelInfo {
     void (*fn)(const ConvParams);
     int block_n, kbox, boxes, smem, mode, ctas;
+    bool px;                 // conv_px_kernel (pixels on N) instead of conv_umma_kernel
 };
 
 template <int BN, int KB, int BX, int ST, int MODE, int CTAS = 2>
@@ -177,11 +179,26 @@ KernelInfo make_kernel() {
     KernelInfo k;
     k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS>;
     k.ctas = CTAS;
+    k.px = false;
     k.block_n = BN;
     k.kbox = KB;
     k.boxes = BX;
     k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS>::kBytes;
     k.mode = MODE;
+    return k;
+}
+
+template <int KB, int ST, int MODE>
+KernelInfo make_px_kernel() {
+    KernelInfo k;
+    k.fn = conv_px_kernel<KB, ST, MODE>;
+    k.block_n = 96;
+    k.kbox = KB;
+    k.boxes = 1;
+    k.smem = PxSmem<KB, ST>::kBytes;
+    k.mode = MODE;
+    k.ctas = 1;
+    k.px = true;
     return k;
 }
 
@@ -200,6 +217,9 @@ const KernelInfo* kernel_table() {
         t[K_POOL256] = make_kernel<256, 64, 1, 6, MODE_POOL>();
         t[K_CONVT256] = make_kernel<256, 64, 1, 4, MODE_CONVT>();
         t[K_N96] = make_kernel<96, 64, 1, 8, MODE_STORE>();     // Cout = 96
+        t[K_PX_STORE] = make_px_kernel<64, 4, MODE_STORE>();            // conv1.0: pixels on N (see conv_px.cuh)
+        t[K_PX_HEAD] = make_px_kernel<64, 4, MODE_HEAD>();              // conv1.2 + outc + scheduler, K padded 96 -> 128 per tap
+        t[K_PX_HEAD32] = make_px_kernel<32, 8, MODE_HEAD>();            // same with exact 32-channel chunks (default)
         t[K_STORE256_1] = make_kernel<256, 64, 1, 3, MODE_STORE, 1>();   // single-CTA variants: A/B measurement only
         t[K_POOL256_1] = make_kernel<256, 64, 1, 4, MODE_POOL, 1>();     // (S1S2_SINGLE_CTA_256=1)
         t[K_HEAD] = make_kernel<96, 32, 3, 6, MODE_HEAD>();     // conv1.2 + outc + scheduler
@@ -283,6 +303,62 @@ int dmalloc(s1s2_handle* h, void** p, size_t bytes, std::string* err) {
     return S1S2_OK;
 }
 
+// conv_px_kernel: pixels (16 x 16 tile of one image) on N, weight rows on M.
+int build_px_params(s1s2_handle* h, Layer& L, const KernelInfo& k, EncodeTiledFn enc, std::string* err) {
+    const int Hl = h->H >> L.level, Wl = h->W >> L.level;
+    if (Hl % 16 != 0 || Wl % 16 != 0 || L.cout > 128 || L.taps_w != 3) {
+        set_err(err, "layer %s: geometry does not fit the pixels-on-N kernel", L.name);
+        return S1S2_ERR_INVALID;
+    }
+    ConvParams& p = L.p;
+    memset(&p, 0, sizeof(p));
+    const CUtensorMapSwizzle sw = swizzle_for(k.kbox);
+    {   // activations: (C, W, H, N), box (kbox, 16, 16, 1); channels past Cin are zero-filled
+        cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cin), static_cast<cuuint64_t>(Wl), static_cast<cuuint64_t>(Hl),
+                              static_cast<cuuint64_t>(h->nalloc)};
+        cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.src_pitch) * 2, static_cast<cuuint64_t>(Wl) * L.src_pitch * 2,
+                                 static_cast<cuuint64_t>(Hl) * Wl * L.src_pitch * 2};
+        cuuint32_t box[4] = {static_cast<cuuint32_t>(k.kbox), 16, 16, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&p.tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(L.src), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_err(err, "layer %s: activation tensor map rejected (CUresult %d)", L.name, static_cast<int>(r)); return S1S2_ERR_CUDA; }
+    }
+    {   // weights: (K, Cout), box (kbox, 128): rows past Cout are zero-filled
+        const int ktot = 9 * L.cin;
+        cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(L.cout)};
+        cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(k.kbox), 128};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&p.tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L.w, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_err(err, "layer %s: weight tensor map rejected (CUresult %d)", L.name, static_cast<int>(r)); return S1S2_ERR_CUDA; }
+    }
+    if (k.mode == MODE_STORE) {
+        cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cout), static_cast<cuuint64_t>(Wl), static_cast<cuuint64_t>(Hl),
+                              static_cast<cuuint64_t>(h->nalloc)};
+        cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.dst_pitch) * 2, static_cast<cuuint64_t>(Wl) * L.dst_pitch * 2,
+                                 static_cast<cuuint64_t>(Hl) * Wl * L.dst_pitch * 2};
+        cuuint32_t box[4] = {32, 16, 8, 1};     // half a tile per store
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&p.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, L.dst, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_err(err, "layer %s: output tensor map rejected (CUresult %d)", L.name, static_cast<int>(r)); return S1S2_ERR_CUDA; }
+    }
+    p.bias = L.bias;
+    p.out = L.dst;
+    p.out_cpitch = L.dst_pitch;
+    p.H = Hl;
+    p.W = Wl;
+    p.taps_w = 3;
+    p.chunks = (L.cin + k.kbox - 1) / k.kbox;
+    p.tap_kstride = L.cin;
+    p.cout = L.cout;
+    p.num_n_tiles = 1;
+    return S1S2_OK;
+}
+
 int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
     const KernelInfo& k = kernel_table()[L.kid];
     EncodeTiledFn enc = get_encode_fn();
@@ -291,6 +367,7 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
         return S1S2_ERR_CUDA;
     }
     const int Hl = h->H >> L.level, Wl = h->W >> L.level;
+    if (k.px) return build_px_params(h, L, k, enc, err);
     const TileGeom g = tile_geom(Hl, Wl);
     const int chunks_ = L.cin / k.kbox;
     const bool boxes_ok = chunks_ == 1 ? (L.taps_w * L.taps_w) % k.boxes == 0 : chunks_ % k.boxes == 0;
@@ -377,6 +454,15 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
 int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, cudaStream_t st, std::string* err) {
     const KernelInfo& k = kernel_table()[L.kid];
     ConvParams& p = L.p;
+    if (k.px) {
+        p.B = B;
+        p.amax_in = amax_in;
+        const int tiles = (p.W >> 4) * (p.H >> 4) * B;
+        k.fn<<<tiles < h->num_sms ? tiles : h->num_sms, 256, k.smem, st>>>(p);
+        CK(cudaGetLastError());
+        ++h->launches;
+        return S1S2_OK;
+    }
     const int tn = 128 >> (p.tw_log2 + p.th_log2);
     p.B = B;
     p.num_m_tiles = p.tiles_x * p.tiles_y * ((B + tn - 1) / tn);
@@ -393,7 +479,7 @@ int run_network(s1s2_handle* h, int B, const HeadParams& head_io, const uint32_t
                 std::string* err) {
     for (size_t i = 0; i < h->layers.size(); ++i) {
         Layer& L = h->layers[i];
-        if (L.kid == K_HEAD) {
+        if (kernel_table()[L.kid].mode == MODE_HEAD) {
             HeadParams& hp = L.p.head;
             memcpy(hp.w, h->head_w, sizeof(hp.w));
             memcpy(hp.b, h->head_b, sizeof(hp.b));
@@ -538,6 +624,12 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     add("conv1.0",     K_N96,    0,  192, 96,   96,  3,   cat1,        192,  c1a,          96);
     add("conv1.2",     K_HEAD,   0,  96,  96,   96,  3,   c1a,         96,   nullptr,      0);
 
+    if (getenv("S1S2_NO_PX") == nullptr) {       // default: pixels-on-N kernels for the Cout = 96 full-resolution layers
+        for (Layer& L : h->layers) {
+            if (L.kid == K_N96) L.kid = K_PX_STORE;
+            if (L.kid == K_HEAD) L.kid = getenv("S1S2_PX_HEAD64") != nullptr ? K_PX_HEAD : K_PX_HEAD32;
+        }
+    }
     if (getenv("S1S2_SINGLE_CTA_256") != nullptr) {
         for (Layer& L : h->layers) {
             if (L.kid == K_STORE256) L.kid = K_STORE256_1;
@@ -788,7 +880,7 @@ int s1s2_debug_loop_layer(s1s2_handle* h, int B, int layer, int reps, int perf_m
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
     Layer& L = h->layers[layer];
-    if (L.kid == K_HEAD) {
+    if (kernel_table()[L.kid].mode == MODE_HEAD) {
         HeadParams& hp = L.p.head;
         memcpy(hp.w, h->head_w, sizeof(hp.w));
         memcpy(hp.b, h->head_b, sizeof(hp.b));
@@ -835,7 +927,7 @@ int s1s2_profile_layers(s1s2_handle* h, int B, int reps, float* ms_out, int n_ou
     for (int r = 0; r < reps; ++r) {
         for (int i = 0; i < nl; ++i) {
             Layer& L = h->layers[i];
-            if (L.kid == K_HEAD) {
+            if (kernel_table()[L.kid].mode == MODE_HEAD) {
                 HeadParams& hp = L.p.head;
                 memcpy(hp.w, h->head_w, sizeof(hp.w));
                 memcpy(hp.b, h->head_b, sizeof(hp.b));

@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB_PATH = os.path.join(HERE, "libs1s2_b200.so")
 SOURCES = ["s1s2_lib.cu"]
-DEPS = ["s1s2_lib.cu", "conv_umma.cuh", "ptx_sm100.cuh", "patch_kernels.cuh",
+DEPS = ["s1s2_lib.cu", "conv_umma.cuh", "conv_px.cuh", "ptx_sm100.cuh", "patch_kernels.cuh",
         os.path.join("..", "..", "include", "s1s2_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
