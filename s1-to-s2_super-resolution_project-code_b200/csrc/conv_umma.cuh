@@ -88,19 +88,30 @@ struct ConvParams {
     HeadParams head;              // MODE_HEAD only
 };
 
-template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS>
+// Halo mode (3x3 layers with Cin % 64 == 0): the M tile is 8 wide x 16 tall and its activations are fetched ONCE per
+// 64-channel chunk as an 18 x 10 pixel halo tile; the nine taps read it through UMMA descriptors whose start address
+// is shifted by (ky*10 + kx) 128-byte rows and whose 8-row-group stride is 10 rows (the hardware applies the 128B
+// swizzle to absolute shared-memory address bits, tools/umma_halo_test.cu).  Activation traffic drops 6.4x.
+constexpr int kHaloW = 10, kHaloH = 18;
+constexpr int kHaloBytes = kHaloW * kHaloH * 128;               // 23040
+constexpr int kHaloSlot = 23 * 1024;                            // 1024-aligned ring slot
+constexpr int kHaloSlots = 3;
+
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false>
 struct ConvSmem {
     static constexpr int kABox = 128 * KBOX * 2;
     static constexpr int kBBox = (BLOCK_N / CTAS) * KBOX * 2;   // this CTA's share of the weight rows
-    static constexpr int kStage = BOXES * (kABox + kBBox);
+    static constexpr int kARing = HALO ? kHaloSlots * kHaloSlot : 0;
+    static constexpr int kStage = HALO ? kBBox : BOXES * (kABox + kBBox);   // halo mode: the ring holds weight tiles only
     // output staging for the TMA store: one [rows][32 channels] fp16 sub-tile (64-byte rows, 64B swizzle) per
     // 32-column accumulator chunk; rows = 128 pixels, or the 32 pooled pixels of the tile
     static constexpr int kSubRows = MODE == MODE_POOL ? 32 : 128;
     static constexpr int kSubBytes = kSubRows * 64;
     static constexpr int kStaging = (MODE != MODE_HEAD) ? (BLOCK_N / 32) * kSubBytes : 0;
     static constexpr int kBias = 1536 * 4;
-    static constexpr int kBytes = 1024 /*align slack*/ + STAGES * kStage + kStaging + kBias + 256 /*barriers*/;
+    static constexpr int kBytes = 1024 /*align slack*/ + kARing + STAGES * kStage + kStaging + kBias + 256 /*barriers*/;
     static_assert(kStage % 512 == 0, "stage alignment");
+    static_assert(!HALO || (KBOX == 64 && BOXES == 1 && STAGES <= 10), "halo mode: 64-channel chunks");
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
@@ -130,10 +141,10 @@ __device__ __forceinline__ float range_scale(uint32_t amax_bits, float& s) {
 
 // CTAS = 2: CTA pair (cta_group::2, M = 256 per MMA, weight rows split across the pair).  CTAS = 1: single-CTA MMAs
 // (M = 128), kept for A/B measurements of the pairing itself.
-template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS>
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false>
 __global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(256, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
-    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE, CTAS>;
+    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE, CTAS, HALO>;
     constexpr bool kPair = CTAS == 2;
     constexpr bool kTmaStore = (MODE != MODE_HEAD);
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
@@ -144,15 +155,18 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stage_base = smem;
-    uint8_t* sout = smem + STAGES * L::kStage;
-    float* sbias = reinterpret_cast<float*>(smem + STAGES * L::kStage + L::kStaging);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage + L::kStaging + L::kBias);
+    uint8_t* a_ring = smem;                       // halo mode: kHaloSlots activation halo tiles
+    uint8_t* stage_base = smem + L::kARing;
+    uint8_t* sout = stage_base + STAGES * L::kStage;
+    float* sbias = reinterpret_cast<float*>(sout + L::kStaging);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sout + L::kStaging + L::kBias);
     uint64_t* full_bar = bars;                    // [STAGES]   (leader's copy is the live one)
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]   (one per CTA, signalled by multicast commits)
     uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]        (one per CTA, multicast commits)
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]        (leader's copy is the live one)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* afull_bar = bars + 2 * STAGES + 4;  // [kHaloSlots] halo mode (leader's copy is the live one)
+    uint64_t* aempty_bar = afull_bar + kHaloSlots;  // [kHaloSlots] halo mode
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + kHaloSlots);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -178,6 +192,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             mbar_init(&tfull_bar[a], 1);        // one multicast commit
             mbar_init(&tempty_bar[a], 4 * CTAS); // one arrive per epilogue warp of every CTA of the group
         }
+        if constexpr (HALO) {
+            for (int a = 0; a < kHaloSlots; ++a) {
+                mbar_init(&afull_bar[a], 1);
+                mbar_init(&aempty_bar[a], 1);
+            }
+        }
         mbar_fence_init();
     }
     if (warp == 2) { if constexpr (kPair) tmem_alloc_pair<512>(tmem_slot); else tmem_alloc<512>(tmem_slot); }
@@ -195,7 +215,94 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     // elected lane issues TMA / MMA / commit).  Uniform control flow lets ptxas keep descriptors and addresses in
     // uniform registers; a `lane == 0` branch around the loops instead costs an R2UR + ELECT + BRA.U.ANY sequence
     // per instruction and made the single issuing thread the bottleneck (~600 cycles per 4-MMA stage).
-    if (warp == 0) {
+    if (HALO && warp == 0) {
+        // ================================================================= TMA producer, halo mode (both CTAs)
+        // flat walk over (tile, chunk): the halo tile of the NEXT (tile, chunk) is requested before the nine weight
+        // tiles of the current one, into the slot freed two positions earlier (never blocks on the MMA warp)
+        int s = 0, sa = 0;
+        uint32_t ph = 0, pha = 0;
+        auto load_halo = [&](int tile, int chunk) {
+            const int m_tile = CTAS * (tile / p.num_n_tiles) + static_cast<int>(rank);
+            const int tx = m_tile % p.tiles_x;
+            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+            const int tn = m_tile / (p.tiles_x * p.tiles_y);       // past the batch for a phantom tile: zero fill
+            mbar_wait(&aempty_bar[sa], pha ^ 1);
+            const uint32_t bar = kPair ? mapa_shared(smem_u32(&afull_bar[sa]), 0) : smem_u32(&afull_bar[sa]);
+            if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(&afull_bar[sa], CTAS * kHaloBytes);
+                tma_load_4d_g<kPair>(a_ring + sa * kHaloSlot, &p.tmap_a, bar, chunk * 64, (tx << 3) - 1, (ty << 4) - 1, tn);
+            }
+            __syncwarp();
+            if (++sa == kHaloSlots) { sa = 0; pha ^= 1; }
+        };
+        int tile = cluster_id, chunk = 0;
+        if (tile < num_tiles) load_halo(tile, 0);
+        while (tile < num_tiles) {
+            int ntile = tile, nchunk = chunk + 1;
+            if (nchunk == p.chunks) { nchunk = 0; ntile += num_clusters; }
+            if (ntile < num_tiles) load_halo(ntile, nchunk);
+            const int b_row0 = (tile % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
+            int kcol = chunk * 64;
+            for (int tap = 0; tap < 9; ++tap, kcol += p.tap_kstride) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const uint32_t bar = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], CTAS * L::kBBox);
+                    tma_load_2d_g<kPair>(stage_base + s * L::kStage, &p.tmap_b, bar, kcol, b_row0);
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            tile = ntile;
+            chunk = nchunk;
+        }
+    } else if (HALO && warp == 1) {
+        // ================================================================= MMA issuer, halo mode (leader CTA)
+        if (rank == 0) {
+            int s = 0, sa = 0;
+            uint32_t ph = 0, pha = 0;
+            int acc = 0;
+            uint32_t acc_ph = 0;
+            const uint32_t b0 = smem_u32(stage_base), a0 = smem_u32(a_ring);
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kAccStride;
+                for (int chunk = 0; chunk < p.chunks; ++chunk) {
+                    mbar_wait(&afull_bar[sa], pha);
+                    const uint32_t a_addr = a0 + sa * kHaloSlot;
+                    // halo descriptor: rows 128 B apart, 8-row groups (= image rows of the 8-wide tile) 10 rows apart
+                    uint64_t adesc0 = static_cast<uint64_t>(1) << 16;
+                    adesc0 |= static_cast<uint64_t>((kHaloW * 128) >> 4) << 32;
+                    adesc0 |= static_cast<uint64_t>(1) << 46;
+                    adesc0 |= 2ull << 61;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const int ky = tap / 3, kx = tap - 3 * ky;
+                        const uint32_t a_tap = a_addr + (ky * kHaloW + kx) * 128;
+                        if (elect_one()) {
+                            const uint64_t adesc = adesc0 | static_cast<uint64_t>((a_tap & 0x3FFFFu) >> 4);
+                            const uint64_t bdesc = umma_smem_desc<128>(b0 + s * L::kStage);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16_g<kPair>(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (chunk | tap | k) != 0 ? 1u : 0u);
+                            umma_commit_g<kPair>(&empty_bar[s]);
+                            if (tap == 8) {
+                                umma_commit_g<kPair>(&aempty_bar[sa]);
+                                if (chunk == p.chunks - 1) umma_commit_g<kPair>(&tfull_bar[acc]);
+                            }
+                        }
+                        __syncwarp();
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                    if (++sa == kHaloSlots) { sa = 0; pha ^= 1; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_ph ^= 1;
+            }
+        }
+    } else if (warp == 0) {
         // ================================================================= TMA producer (both CTAs)
         int s = 0;
         uint32_t ph = 0;

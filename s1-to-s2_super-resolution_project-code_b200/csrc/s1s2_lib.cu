@@ -166,24 +166,26 @@ CUtensorMapSwizzle swizzle_for(int kbox) {
 }
 
 // ---------------------------------------------------------------------------------------------- layers
-enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_STORE256_1, K_POOL256_1, K_PX_STORE, K_PX_HEAD, K_PX_HEAD32, K_COUNT };
+enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_STORE256_1, K_POOL256_1, K_PX_STORE, K_PX_HEAD, K_PX_HEAD32, K_HSTORE, K_HPOOL, K_HSTORE256, K_HPOOL256, K_COUNT };
 
 struct KernelInfo {
     void (*fn)(const ConvParams);
     int block_n, kbox, boxes, smem, mode, ctas;
     bool px;                 // conv_px_kernel (pixels on N) instead of conv_umma_kernel
+    bool halo;               // conv_umma_kernel halo mode (8 x 16 tile, one activation halo tile per chunk)
 };
 
-template <int BN, int KB, int BX, int ST, int MODE, int CTAS = 2>
+template <int BN, int KB, int BX, int ST, int MODE, int CTAS = 2, bool HALO = false>
 KernelInfo make_kernel() {
     KernelInfo k;
-    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS>;
+    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS, HALO>;
     k.ctas = CTAS;
     k.px = false;
+    k.halo = HALO;
     k.block_n = BN;
     k.kbox = KB;
     k.boxes = BX;
-    k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS>::kBytes;
+    k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS, HALO>::kBytes;
     k.mode = MODE;
     return k;
 }
@@ -199,6 +201,7 @@ KernelInfo make_px_kernel() {
     k.mode = MODE;
     k.ctas = 1;
     k.px = true;
+    k.halo = false;
     return k;
 }
 
@@ -217,6 +220,10 @@ const KernelInfo* kernel_table() {
         t[K_POOL256] = make_kernel<256, 64, 1, 6, MODE_POOL>();
         t[K_CONVT256] = make_kernel<256, 64, 1, 4, MODE_CONVT>();
         t[K_N96] = make_kernel<96, 64, 1, 8, MODE_STORE>();     // Cout = 96
+        t[K_HSTORE] = make_kernel<192, 64, 1, 8, MODE_STORE, 2, true>();    // halo mode (default for 3x3, Cin % 64 == 0)
+        t[K_HPOOL] = make_kernel<192, 64, 1, 10, MODE_POOL, 2, true>();
+        t[K_HSTORE256] = make_kernel<256, 64, 1, 5, MODE_STORE, 2, true>();
+        t[K_HPOOL256] = make_kernel<256, 64, 1, 8, MODE_POOL, 2, true>();
         t[K_PX_STORE] = make_px_kernel<64, 4, MODE_STORE>();            // conv1.0: pixels on N (see conv_px.cuh)
         t[K_PX_HEAD] = make_px_kernel<64, 4, MODE_HEAD>();              // conv1.2 + outc + scheduler, K padded 96 -> 128 per tap
         t[K_PX_HEAD32] = make_px_kernel<32, 8, MODE_HEAD>();            // same with exact 32-channel chunks (default)
@@ -368,7 +375,14 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
     }
     const int Hl = h->H >> L.level, Wl = h->W >> L.level;
     if (k.px) return build_px_params(h, L, k, enc, err);
-    const TileGeom g = tile_geom(Hl, Wl);
+    TileGeom g = tile_geom(Hl, Wl);
+    if (k.halo) {            // 8 wide x 16 tall tile of one image; partial tiles are zero-filled on load, clipped on store
+        g.tw_log2 = 3;
+        g.th_log2 = 4;
+        g.tn = 1;
+        g.tiles_x = (Wl + 7) / 8;
+        g.tiles_y = (Hl + 15) / 16;
+    }
     const int chunks_ = L.cin / k.kbox;
     const bool boxes_ok = chunks_ == 1 ? (L.taps_w * L.taps_w) % k.boxes == 0 : chunks_ % k.boxes == 0;
     if (L.cin % k.kbox != 0 || !boxes_ok || L.ntot % k.block_n != 0) {
@@ -384,6 +398,7 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
                                  static_cast<cuuint64_t>(Hl) * Wl * L.src_pitch * 2};
         cuuint32_t box[4] = {static_cast<cuuint32_t>(k.kbox), 1u << g.tw_log2, 1u << g.th_log2,
                              static_cast<cuuint32_t>(g.tn)};
+        if (k.halo) { box[1] = kHaloW; box[2] = kHaloH; }        // tile + 1-pixel ring, fetched once per channel chunk
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&p.tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(L.src), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(k.kbox), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -446,6 +461,7 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
     p.num_n_tiles = L.ntot / k.block_n;
     p.taps_w = L.taps_w;
     p.chunks = L.cin / k.kbox;
+    p.tap_kstride = L.cin;
     p.cout = L.cout;
     p.flags = L.kid == K_INC ? LAYER_FLAG_FIRST : 0;
     return S1S2_OK;
@@ -624,6 +640,15 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     add("conv1.0",     K_N96,    0,  192, 96,   96,  3,   cat1,        192,  c1a,          96);
     add("conv1.2",     K_HEAD,   0,  96,  96,   96,  3,   c1a,         96,   nullptr,      0);
 
+    if (getenv("S1S2_NO_HALO") == nullptr) {
+        for (Layer& L : h->layers) {
+            if (L.taps_w != 3 || L.cin % 64 != 0) continue;
+            if (L.kid == K_STORE) L.kid = K_HSTORE;
+            else if (L.kid == K_POOL) L.kid = K_HPOOL;
+            else if (L.kid == K_STORE256) L.kid = K_HSTORE256;
+            else if (L.kid == K_POOL256) L.kid = K_HPOOL256;
+        }
+    }
     if (getenv("S1S2_NO_PX") == nullptr) {       // default: pixels-on-N kernels for the Cout = 96 full-resolution layers
         for (Layer& L : h->layers) {
             if (L.kid == K_N96) L.kid = K_PX_STORE;
