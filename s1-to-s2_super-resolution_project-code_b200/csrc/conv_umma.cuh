@@ -93,25 +93,30 @@ struct ConvParams {
 // is shifted by (ky*10 + kx) 128-byte rows and whose 8-row-group stride is 10 rows (the hardware applies the 128B
 // swizzle to absolute shared-memory address bits, tools/umma_halo_test.cu).  Activation traffic drops 6.4x.
 constexpr int kHaloW = 10, kHaloH = 18;
-constexpr int kHaloBytes = kHaloW * kHaloH * 128;               // 23040
-constexpr int kHaloSlot = 23 * 1024;                            // 1024-aligned ring slot
 constexpr int kHaloSlots = 3;
+template <int KBOX>
+struct Halo {                                                   // KBOX channels per pixel row: 128 / 64 / 32-byte rows
+    static constexpr int kBytes = kHaloW * kHaloH * KBOX * 2;   // 23040 at KBOX = 64
+    static constexpr int kSlot = (kBytes + 1023) / 1024 * 1024; // 1024-aligned ring slot
+};
 
-template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false>
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, int SBUF = 1>
 struct ConvSmem {
     static constexpr int kABox = 128 * KBOX * 2;
     static constexpr int kBBox = (BLOCK_N / CTAS) * KBOX * 2;   // this CTA's share of the weight rows
-    static constexpr int kARing = HALO ? kHaloSlots * kHaloSlot : 0;
+    static constexpr int kARing = HALO ? kHaloSlots * Halo<KBOX>::kSlot : 0;
     static constexpr int kStage = HALO ? kBBox : BOXES * (kABox + kBBox);   // halo mode: the ring holds weight tiles only
     // output staging for the TMA store: one [rows][32 channels] fp16 sub-tile (64-byte rows, 64B swizzle) per
     // 32-column accumulator chunk; rows = 128 pixels, or the 32 pooled pixels of the tile
     static constexpr int kSubRows = MODE == MODE_POOL ? 32 : 128;
     static constexpr int kSubBytes = kSubRows * 64;
-    static constexpr int kStaging = (MODE != MODE_HEAD) ? (BLOCK_N / 32) * kSubBytes : 0;
+    static constexpr int kStagingBuf = (MODE != MODE_HEAD) ? (BLOCK_N / 32) * kSubBytes : 0;
+    static constexpr int kStaging = SBUF * kStagingBuf;       // SBUF > 1: short-K layers, where a tile is shorter than a
+                                                              // TMA store's smem-read latency
     static constexpr int kBias = 1536 * 4;
     static constexpr int kBytes = 1024 /*align slack*/ + kARing + STAGES * kStage + kStaging + kBias + 256 /*barriers*/;
     static_assert(kStage % 512 == 0, "stage alignment");
-    static_assert(!HALO || (KBOX == 64 && BOXES == 1 && STAGES <= 10), "halo mode: 64-channel chunks");
+    static_assert(!HALO || (BOXES == 1 && STAGES <= 10), "halo mode");
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
@@ -141,10 +146,13 @@ __device__ __forceinline__ float range_scale(uint32_t amax_bits, float& s) {
 
 // CTAS = 2: CTA pair (cta_group::2, M = 256 per MMA, weight rows split across the pair).  CTAS = 1: single-CTA MMAs
 // (M = 128), kept for A/B measurements of the pairing itself.
-template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false>
+// WRES (halo mode, one chunk per tap, STAGES >= 9): the nine weight tiles are loaded once per CTA and stay resident;
+// the ring then only carries activation halo tiles (inc.0: K = 16 per tap would otherwise be TMA-latency bound).
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, bool WRES = false, int SBUF = 1>
 __global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(256, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
-    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE, CTAS, HALO>;
+    static_assert(!WRES || (HALO && STAGES >= 9), "resident weights need halo mode and nine slots");
+    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE, CTAS, HALO, SBUF>;
     constexpr bool kPair = CTAS == 2;
     constexpr bool kTmaStore = (MODE != MODE_HEAD);
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
@@ -157,9 +165,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;                       // halo mode: kHaloSlots activation halo tiles
     uint8_t* stage_base = smem + L::kARing;
-    uint8_t* sout = stage_base + STAGES * L::kStage;
-    float* sbias = reinterpret_cast<float*>(sout + L::kStaging);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sout + L::kStaging + L::kBias);
+    uint8_t* sout0 = stage_base + STAGES * L::kStage;
+    float* sbias = reinterpret_cast<float*>(sout0 + L::kStaging);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sout0 + L::kStaging + L::kBias);
     uint64_t* full_bar = bars;                    // [STAGES]   (leader's copy is the live one)
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]   (one per CTA, signalled by multicast commits)
     uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]        (one per CTA, multicast commits)
@@ -229,21 +237,32 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             mbar_wait(&aempty_bar[sa], pha ^ 1);
             const uint32_t bar = kPair ? mapa_shared(smem_u32(&afull_bar[sa]), 0) : smem_u32(&afull_bar[sa]);
             if (elect_one()) {
-                if (rank == 0) mbar_expect_tx(&afull_bar[sa], CTAS * kHaloBytes);
-                tma_load_4d_g<kPair>(a_ring + sa * kHaloSlot, &p.tmap_a, bar, chunk * 64, (tx << 3) - 1, (ty << 4) - 1, tn);
+                if (rank == 0) mbar_expect_tx(&afull_bar[sa], CTAS * Halo<KBOX>::kBytes);
+                tma_load_4d_g<kPair>(a_ring + sa * Halo<KBOX>::kSlot, &p.tmap_a, bar, chunk * KBOX, (tx << 3) - 1, (ty << 4) - 1, tn);
             }
             __syncwarp();
             if (++sa == kHaloSlots) { sa = 0; pha ^= 1; }
         };
         int tile = cluster_id, chunk = 0;
+        if constexpr (WRES) {                     // one N tile, one chunk per tap: all weights of the layer, once
+            for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t bar = kPair ? mapa_shared(smem_u32(&full_bar[tap]), 0) : smem_u32(&full_bar[tap]);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(&full_bar[tap], CTAS * L::kBBox);
+                    tma_load_2d_g<kPair>(stage_base + tap * L::kStage, &p.tmap_b, bar, tap * p.tap_kstride,
+                                         static_cast<int>(rank) * (BLOCK_N / CTAS));
+                }
+                __syncwarp();
+            }
+        }
         if (tile < num_tiles) load_halo(tile, 0);
         while (tile < num_tiles) {
             int ntile = tile, nchunk = chunk + 1;
             if (nchunk == p.chunks) { nchunk = 0; ntile += num_clusters; }
             if (ntile < num_tiles) load_halo(ntile, nchunk);
             const int b_row0 = (tile % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
-            int kcol = chunk * 64;
-            for (int tap = 0; tap < 9; ++tap, kcol += p.tap_kstride) {
+            int kcol = chunk * KBOX;
+            for (int tap = 0; tap < (WRES ? 0 : 9); ++tap, kcol += p.tap_kstride) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 const uint32_t bar = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
                 if (elect_one()) {
@@ -270,31 +289,32 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 const uint32_t d_tmem = tmem_base + acc * kAccStride;
                 for (int chunk = 0; chunk < p.chunks; ++chunk) {
                     mbar_wait(&afull_bar[sa], pha);
-                    const uint32_t a_addr = a0 + sa * kHaloSlot;
-                    // halo descriptor: rows 128 B apart, 8-row groups (= image rows of the 8-wide tile) 10 rows apart
+                    const uint32_t a_addr = a0 + sa * Halo<KBOX>::kSlot;
+                    // halo descriptor: rows kRowBytes apart, 8-row groups (= image rows of the 8-wide tile) 10 rows apart
                     uint64_t adesc0 = static_cast<uint64_t>(1) << 16;
-                    adesc0 |= static_cast<uint64_t>((kHaloW * 128) >> 4) << 32;
+                    adesc0 |= static_cast<uint64_t>((kHaloW * kRowBytes) >> 4) << 32;
                     adesc0 |= static_cast<uint64_t>(1) << 46;
-                    adesc0 |= 2ull << 61;
+                    adesc0 |= (kRowBytes == 128 ? 2ull : (kRowBytes == 64 ? 4ull : 6ull)) << 61;
                     for (int tap = 0; tap < 9; ++tap) {
+                        if constexpr (WRES) { s = tap; ph = 0; }      // resident weights: phase 0 completed once, for good
                         mbar_wait(&full_bar[s], ph);
                         tc_fence_after();
                         const int ky = tap / 3, kx = tap - 3 * ky;
-                        const uint32_t a_tap = a_addr + (ky * kHaloW + kx) * 128;
+                        const uint32_t a_tap = a_addr + (ky * kHaloW + kx) * kRowBytes;
                         if (elect_one()) {
                             const uint64_t adesc = adesc0 | static_cast<uint64_t>((a_tap & 0x3FFFFu) >> 4);
-                            const uint64_t bdesc = umma_smem_desc<128>(b0 + s * L::kStage);
+                            const uint64_t bdesc = umma_smem_desc<kRowBytes>(b0 + s * L::kStage);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
+                            for (int k = 0; k < KBOX / 16; ++k)
                                 umma_f16_g<kPair>(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (chunk | tap | k) != 0 ? 1u : 0u);
-                            umma_commit_g<kPair>(&empty_bar[s]);
+                            if constexpr (!WRES) umma_commit_g<kPair>(&empty_bar[s]);
                             if (tap == 8) {
                                 umma_commit_g<kPair>(&aempty_bar[sa]);
                                 if (chunk == p.chunks - 1) umma_commit_g<kPair>(&tfull_bar[acc]);
                             }
                         }
                         __syncwarp();
-                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                        if constexpr (!WRES) { if (++s == STAGES) { s = 0; ph ^= 1; } }
                     }
                     if (++sa == kHaloSlots) { sa = 0; pha ^= 1; }
                 }
@@ -398,7 +418,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         const int ln = m >> (p.tw_log2 + p.th_log2);
         int acc = 0;
         uint32_t acc_ph = 0;
+        int sbuf = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            uint8_t* sout = sout0 + sbuf * L::kStagingBuf;
+            if (++sbuf == SBUF) sbuf = 0;
             const int n_tile = tile % p.num_n_tiles;
             const int m_tile = CTAS * (tile / p.num_n_tiles) + static_cast<int>(rank);
             const int tx = m_tile % p.tiles_x;
@@ -510,7 +533,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     srow = ((ln << (p.th_log2 - 1)) + (ly >> 1)) * (tw >> 1) + (lx >> 1);
                 }
                 if constexpr (kTmaStore) {
-                    if (warp == 4 && lane == 0) bulk_wait_read0();      // previous tile's stores have read the staging
+                    if (warp == 4 && lane == 0) bulk_wait_read<SBUF - 1>();   // this buffer's previous stores have read it
                     named_bar_sync(1, 128);
                 }
                 const bool first = (p.flags & LAYER_FLAG_FIRST) != 0;

@@ -166,7 +166,7 @@ CUtensorMapSwizzle swizzle_for(int kbox) {
 }
 
 // ---------------------------------------------------------------------------------------------- layers
-enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_STORE256_1, K_POOL256_1, K_PX_STORE, K_PX_HEAD, K_PX_HEAD32, K_HSTORE, K_HPOOL, K_HSTORE256, K_HPOOL256, K_COUNT };
+enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_STORE256_1, K_POOL256_1, K_PX_STORE, K_PX_HEAD, K_PX_HEAD32, K_HSTORE, K_HPOOL, K_HSTORE256, K_HPOOL256, K_HINC, K_HC96IN, K_COUNT };
 
 struct KernelInfo {
     void (*fn)(const ConvParams);
@@ -175,17 +175,17 @@ struct KernelInfo {
     bool halo;               // conv_umma_kernel halo mode (8 x 16 tile, one activation halo tile per chunk)
 };
 
-template <int BN, int KB, int BX, int ST, int MODE, int CTAS = 2, bool HALO = false>
+template <int BN, int KB, int BX, int ST, int MODE, int CTAS = 2, bool HALO = false, bool WRES = false, int SBUF = 1>
 KernelInfo make_kernel() {
     KernelInfo k;
-    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS, HALO>;
+    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS, HALO, WRES, SBUF>;
     k.ctas = CTAS;
     k.px = false;
     k.halo = HALO;
     k.block_n = BN;
     k.kbox = KB;
     k.boxes = BX;
-    k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS, HALO>::kBytes;
+    k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS, HALO, SBUF>::kBytes;
     k.mode = MODE;
     return k;
 }
@@ -224,6 +224,8 @@ const KernelInfo* kernel_table() {
         t[K_HPOOL] = make_kernel<192, 64, 1, 10, MODE_POOL, 2, true>();
         t[K_HSTORE256] = make_kernel<256, 64, 1, 5, MODE_STORE, 2, true>();
         t[K_HPOOL256] = make_kernel<256, 64, 1, 8, MODE_POOL, 2, true>();
+        t[K_HINC] = make_kernel<96, 16, 1, 9, MODE_STORE, 2, true, true, 4>();  // inc.0: 32-byte rows, resident weights, 4 staging buffers
+        t[K_HC96IN] = make_kernel<192, 32, 1, 10, MODE_STORE, 2, true>();   // down1.0.0: Cin = 96 as three 32-channel chunks
         t[K_PX_STORE] = make_px_kernel<64, 4, MODE_STORE>();            // conv1.0: pixels on N (see conv_px.cuh)
         t[K_PX_HEAD] = make_px_kernel<64, 4, MODE_HEAD>();              // conv1.2 + outc + scheduler, K padded 96 -> 128 per tap
         t[K_PX_HEAD32] = make_px_kernel<32, 8, MODE_HEAD>();            // same with exact 32-channel chunks (default)
@@ -463,7 +465,7 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
     p.chunks = L.cin / k.kbox;
     p.tap_kstride = L.cin;
     p.cout = L.cout;
-    p.flags = L.kid == K_INC ? LAYER_FLAG_FIRST : 0;
+    p.flags = (L.kid == K_INC || L.kid == K_HINC) ? LAYER_FLAG_FIRST : 0;
     return S1S2_OK;
 }
 
@@ -642,7 +644,10 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
 
     if (getenv("S1S2_NO_HALO") == nullptr) {
         for (Layer& L : h->layers) {
-            if (L.taps_w != 3 || L.cin % 64 != 0) continue;
+            if (L.taps_w != 3) continue;
+            if (L.kid == K_INC) L.kid = K_HINC;
+            else if (L.kid == K_C96IN && getenv("S1S2_HALO_C96") != nullptr) L.kid = K_HC96IN;   // measured slower (small stages)
+            if (L.cin % 64 != 0) continue;
             if (L.kid == K_STORE) L.kid = K_HSTORE;
             else if (L.kid == K_POOL) L.kid = K_HPOOL;
             else if (L.kid == K_STORE256) L.kid = K_HSTORE256;
@@ -724,7 +729,7 @@ int s1s2_load_weights(s1s2_handle* h, int n, const char* const* names, const flo
         const float *w = nullptr, *b = nullptr;
         const std::string nm = L.name;
         int rc;
-        if (L.kid == K_INC) {
+        if ((L.kid == K_INC || L.kid == K_HINC)) {
             if ((rc = find(nm + ".weight", 96 * 9 * 9, &w)) || (rc = find(nm + ".bias", 96, &b))) return rc;
             repack_inc_kernel<<<64, 256, 0, st>>>(w, L.w, 96);
             tile_bias_kernel<<<4, 256, 0, st>>>(b, L.bias, 96, 1);

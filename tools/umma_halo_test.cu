@@ -9,7 +9,11 @@
 using namespace s1s2;
 
 constexpr int TW = 8, TH = 16, HW_ = TW + 2, HH_ = TH + 2;     // output tile 8 x 16, halo tile 10 x 18
-constexpr int IMG_W = 16, IMG_H = 24, C = 64, NOUT = 32;
+#ifndef CH
+#define CH 64
+#endif
+constexpr int IMG_W = 16, IMG_H = 24, C = CH, NOUT = 32;
+constexpr int ROWB = C * 2;                                   // bytes per K-major row: 128 (SW128) or 64 (SW64)
 
 struct P { CUtensorMap ta, tb; float* out; int variant; };
 
@@ -27,24 +31,24 @@ __global__ void __launch_bounds__(128, 1) k(const __grid_constant__ P p) {
     tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t tmem = *slot;
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, HW_ * HH_ * 128 + 9 * 4096);
+        mbar_expect_tx(bar, HW_ * HH_ * ROWB + 9 * NOUT * ROWB);
         tma_load_4d(sa, &p.ta, bar, 0, 4 - 1, 3 - 1, 0);          // tile origin (x=4, y=3): halo starts at (3, 2)
-        for (int t = 0; t < 9; ++t) tma_load_2d(sb + t * 4096, &p.tb, bar, t * C, 0);
+        for (int t = 0; t < 9; ++t) tma_load_2d(sb + t * 4096, &p.tb, bar, t * C, 0);   // 4096-byte slots either way
         mbar_wait(bar, 0);
         tc_fence_after();
         const uint32_t idesc = umma_idesc_f16(128, NOUT);
         for (int t = 0; t < 9; ++t) {
             const int ky = t / 3, kx = t % 3;
-            const uint32_t start = smem_u32(sa) + (ky * HW_ + kx) * 128;
+            const uint32_t start = smem_u32(sa) + (ky * HW_ + kx) * ROWB;
             uint64_t ad = 0;
             ad |= static_cast<uint64_t>((start & 0x3FFFFu) >> 4);
             ad |= static_cast<uint64_t>(1) << 16;
-            ad |= static_cast<uint64_t>((HW_ * 128) >> 4) << 32;                     // SBO = 1280 bytes
+            ad |= static_cast<uint64_t>((HW_ * ROWB) >> 4) << 32;                    // SBO = 10 rows
             ad |= static_cast<uint64_t>(1) << 46;
             if (p.variant == 1) ad |= static_cast<uint64_t>((start >> 7) & 7) << 49;  // matrix base offset
-            ad |= 2ull << 61;
-            const uint64_t bd = umma_smem_desc<128>(smem_u32(sb + t * 4096));
-            for (int kk = 0; kk < 4; ++kk) umma_f16(tmem + t * NOUT, ad + 2 * kk, bd + 2 * kk, idesc, kk != 0);
+            ad |= (ROWB == 128 ? 2ull : 4ull) << 61;
+            const uint64_t bd = umma_smem_desc<ROWB>(smem_u32(sb + t * 4096));
+            for (int kk = 0; kk < C / 16; ++kk) umma_f16(tmem + t * NOUT, ad + 2 * kk, bd + 2 * kk, idesc, kk != 0);
         }
         umma_commit(bar2);
     }
@@ -81,11 +85,11 @@ int main() {
     { cuuint64_t d[4] = {C, IMG_W, IMG_H, 1}; cuuint64_t s[3] = {C * 2, IMG_W * C * 2, (cuuint64_t)IMG_H * IMG_W * C * 2};
       cuuint32_t b[4] = {C, HW_, HH_, 1}; cuuint32_t e[4] = {1, 1, 1, 1};
       CUresult r = enc(&p.ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, da, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                       (C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r) { printf("tmap a %d\n", (int)r); return 1; } }
     { cuuint64_t d[2] = {9 * C, NOUT}; cuuint64_t s[1] = {9 * C * 2}; cuuint32_t b[2] = {C, NOUT}; cuuint32_t e[2] = {1, 1};
       CUresult r = enc(&p.tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, db, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                       (C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r) { printf("tmap b %d\n", (int)r); return 1; } }
     p.out = dout;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
