@@ -7,8 +7,10 @@
 //   D^T[cout, pixel] = sum_{tap, cin} Wt[cout, tap, cin] * X[pixel shifted by tap, cin]
 //
 // M = 128 weight rows (96 real; the TMA box overhangs the 96-row weight tensor and the overhang is zero-filled), N = 256
-// pixels = one 16 x 16 spatial tile of one image, K chunks of KBOX channels per tap.  Same TMA boxes, swizzles and UMMA
-// descriptors as conv_umma_kernel with the operand roles swapped; single CTA (cta_group::1).
+// pixels = one 8 wide x 32 tall spatial tile of one image, K chunks of KBOX channels per tap.  Halo mode like
+// conv_umma_kernel: the pixel operand of a channel chunk is ONE 34 x 10 halo tile that all nine taps read through
+// shifted descriptors (8-row groups = image rows, 10 rows apart); only the weight tiles stream per tap.  Same swizzles
+// and UMMA descriptors as conv_umma_kernel with the operand roles swapped; single CTA (cta_group::1).
 //
 // Epilogue: a thread owns one output channel (TMEM lane) and sees the tile's 256 pixels as columns.  bias + ReLU in
 // fp32, then the tile is transposed through shared memory, half a tile (8 image rows) at a time to keep the staging at
@@ -22,15 +24,20 @@
 
 namespace s1s2 {
 
+constexpr int kPxHaloW = 10, kPxHaloH = 34, kPxHaloSlots = 2;
+
 template <int KBOX, int STAGES>
 struct PxSmem {
     static constexpr int kABox = 128 * KBOX * 2;        // weights: 128 rows (cout, zero-padded past the real rows)
-    static constexpr int kBBox = 256 * KBOX * 2;        // pixels: 16 x 16 tile
-    static constexpr int kStage = kABox + kBBox;
+    static constexpr int kHaloBytes = kPxHaloW * kPxHaloH * KBOX * 2;          // pixels: 8 x 32 tile + 1-pixel ring
+    static constexpr int kHaloSlot = (kHaloBytes + 1023) / 1024 * 1024;
+    static constexpr int kHaloRing = kPxHaloSlots * kHaloSlot;
+    static constexpr int kStage = kABox;                // the ring streams weight tiles only
     static constexpr int kSubBytes = 128 * 64;          // [128 pixels = half a tile][32 ch] fp16, 64B swizzle
     static constexpr int kStaging = 3 * kSubBytes;
     static constexpr int kBias = 128 * 4;
-    static constexpr int kBytes = 1024 + STAGES * kStage + kStaging + kBias + 256;
+    static constexpr int kBytes = 1024 + kHaloRing + STAGES * kStage + kStaging + kBias + 256;
+    static_assert(STAGES >= 2 && STAGES <= 10, "weight ring depth");
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
@@ -44,21 +51,23 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stage_base = smem;
-    uint8_t* sout = smem + STAGES * L::kStage;
+    uint8_t* halo_ring = smem;
+    uint8_t* stage_base = smem + L::kHaloRing;
+    uint8_t* sout = stage_base + STAGES * L::kStage;
     float* sbias = reinterpret_cast<float*>(sout + L::kStaging);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sout + L::kStaging + L::kBias);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tfull_bar = bars + 2 * STAGES;
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* hfull_bar = bars + 2 * STAGES + 4;      // [kPxHaloSlots]
+    uint64_t* hempty_bar = hfull_bar + kPxHaloSlots;  // [kPxHaloSlots]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty_bar + kPxHaloSlots);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tiles_x = p.W >> 4, tiles_y = p.H >> 4;
+    const int tiles_x = p.W >> 3, tiles_y = (p.H + 31) >> 5;
     const int num_tiles = tiles_x * tiles_y * p.B;
-    const int k_iters = 9 * p.chunks;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmap_a);
@@ -74,6 +83,10 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], 4);
         }
+        for (int a = 0; a < kPxHaloSlots; ++a) {
+            mbar_init(&hfull_bar[a], 1);
+            mbar_init(&hempty_bar[a], 1);
+        }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -85,59 +98,82 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
 
     if (warp == 0) {
         // ================================================================= TMA producer
-        int s = 0;
-        uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // flat walk over (tile, chunk).  With two halo slots the NEXT halo tile is requested after weight tile kIssueTap
+        // of the current chunk: by then the MMA warp (at most STAGES weight tiles behind) is done with the slot's
+        // previous occupant, so the request never blocks the weight stream.
+        constexpr int kIssueTap = STAGES - 1 < 8 ? STAGES - 1 : 8;
+        int s = 0, sh = 0;
+        uint32_t ph = 0, phh = 0;
+        auto load_halo = [&](int tile, int chunk) {
             const int tx = tile % tiles_x;
             const int ty = (tile / tiles_x) % tiles_y;
             const int n = tile / (tiles_x * tiles_y);
-            const int x0 = (tx << 4) - 1, y0 = (ty << 4) - 1;
-            int chunk = 0, kx = 0, ky = 0, kcol = 0;
-            for (int it = 0; it < k_iters; ++it) {
+            mbar_wait(&hempty_bar[sh], phh ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(&hfull_bar[sh], L::kHaloBytes);
+                tma_load_4d(halo_ring + sh * L::kHaloSlot, &p.tmap_a, &hfull_bar[sh], chunk * KBOX, (tx << 3) - 1, (ty << 5) - 1, n);
+            }
+            __syncwarp();
+            if (++sh == kPxHaloSlots) { sh = 0; phh ^= 1; }
+        };
+        int tile = blockIdx.x, chunk = 0;
+        if (tile < num_tiles) load_halo(tile, 0);
+        while (tile < num_tiles) {
+            int ntile = tile, nchunk = chunk + 1;
+            if (nchunk == p.chunks) { nchunk = 0; ntile += gridDim.x; }
+            int kcol = chunk * KBOX;
+            for (int tap = 0; tap < 9; ++tap, kcol += p.tap_kstride) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* a_dst = stage_base + s * L::kStage;
                 if (elect_one()) {
-                    mbar_expect_tx(&full_bar[s], L::kStage);
-                    tma_load_2d(a_dst, &p.tmap_b, &full_bar[s], kcol, 0);                                   // weights
-                    tma_load_4d(a_dst + L::kABox, &p.tmap_a, &full_bar[s], chunk * KBOX, x0 + kx, y0 + ky, n);  // pixels
+                    mbar_expect_tx(&full_bar[s], L::kABox);
+                    tma_load_2d(stage_base + s * L::kStage, &p.tmap_b, &full_bar[s], kcol, 0);
                 }
                 __syncwarp();
-                if (++chunk == p.chunks) {
-                    chunk = 0;
-                    kcol += p.tap_kstride - (p.chunks - 1) * KBOX;      // first K column of the next tap
-                    if (++kx == 3) { kx = 0; ++ky; }
-                } else {
-                    kcol += KBOX;
-                }
                 if (++s == STAGES) { s = 0; ph ^= 1; }
+                if (tap == kIssueTap && ntile < num_tiles) load_halo(ntile, nchunk);
             }
+            tile = ntile;
+            chunk = nchunk;
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer
-        int s = 0;
-        uint32_t ph = 0;
+        int s = 0, sh = 0;
+        uint32_t ph = 0, phh = 0;
         int acc = 0;
         uint32_t acc_ph = 0;
-        const uint32_t stage0 = smem_u32(stage_base);
+        const uint32_t w0 = smem_u32(stage_base), h0 = smem_u32(halo_ring);
+        uint64_t bdesc0 = static_cast<uint64_t>(1) << 16;            // pixel operand: rows kRowBytes apart, groups 10 rows apart
+        bdesc0 |= static_cast<uint64_t>((kPxHaloW * kRowBytes) >> 4) << 32;
+        bdesc0 |= static_cast<uint64_t>(1) << 46;
+        bdesc0 |= (kRowBytes == 128 ? 2ull : (kRowBytes == 64 ? 4ull : 6ull)) << 61;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * kAccStride;
-            for (int it = 0; it < k_iters; ++it) {
-                mbar_wait(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t w_addr = stage0 + s * L::kStage;
-                if (elect_one()) {
-                    const uint64_t adesc = umma_smem_desc<kRowBytes>(w_addr);                 // M side: weights
-                    const uint64_t bdesc = umma_smem_desc<kRowBytes>(w_addr + L::kABox);      // N side: pixels
+            for (int chunk = 0; chunk < p.chunks; ++chunk) {
+                mbar_wait(&hfull_bar[sh], phh);
+                const uint32_t h_addr = h0 + sh * L::kHaloSlot;
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const int ky = tap / 3, kx = tap - 3 * ky;
+                    const uint32_t h_tap = h_addr + (ky * kPxHaloW + kx) * kRowBytes;
+                    if (elect_one()) {
+                        const uint64_t adesc = umma_smem_desc<kRowBytes>(w0 + s * L::kStage);                    // M side: weights
+                        const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((h_tap & 0x3FFFFu) >> 4);       // N side: pixels
 #pragma unroll
-                    for (int k = 0; k < KBOX / 16; ++k)
-                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (it | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty_bar[s]);
-                    if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+                        for (int k = 0; k < KBOX / 16; ++k)
+                            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (chunk | tap | k) != 0 ? 1u : 0u);
+                        umma_commit(&empty_bar[s]);
+                        if (tap == 8) {
+                            umma_commit(&hempty_bar[sh]);
+                            if (chunk == p.chunks - 1) umma_commit(&tfull_bar[acc]);
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                __syncwarp();
-                if (++s == STAGES) { s = 0; ph ^= 1; }
+                if (++sh == kPxHaloSlots) { sh = 0; phh ^= 1; }
             }
             acc ^= 1;
             if (acc == 0) acc_ph ^= 1;
@@ -196,14 +232,15 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
                     if (warp == 4 && lane == 0) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
-                            tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, c * 32, tx << 4, (ty << 4) + half * 8, n);
+                            tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, c * 32, tx << 3, (ty << 5) + half * 16, n);
                         bulk_commit();
                     }
                 } else {
                     named_bar_sync(1, 128);                          // hidden half tile complete in shared memory
                     // pass 2: this thread's pixel: outc over the 96 hidden channels, scheduler update, writes
                     const int px = et;
-                    const int x = (tx << 4) + (px & 15), y = (ty << 4) + half * 8 + (px >> 4);
+                    const int x = (tx << 3) + (px & 7), y = (ty << 5) + half * 16 + (px >> 3);
+                    const bool inside = y < p.H;                 // H % 32 == 16: the tile's lower half is outside the image
                     float o[kHeadOut];
 #pragma unroll
                     for (int k = 0; k < kHeadOut; ++k) o[k] = p.head.b[k] * s_dn;
@@ -228,6 +265,7 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
                     }
                     const size_t pix = static_cast<size_t>(y) * p.W + x;
                     float res[kHeadOut];
+                    if (inside) {
 #pragma unroll
                     for (int k = 0; k < kHeadOut; ++k) {
                         const size_t idx = (static_cast<size_t>(n) * kHeadOut + k) * plane + pix;
@@ -268,6 +306,7 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
                         u.x = pack_half2_sat(hi[0], hi[1]);
                         u.y = pack_half2_sat(hi[2], hi[3]);
                         *reinterpret_cast<uint2*>(rec + 12) = u;
+                    }
                     }
                 }
             }

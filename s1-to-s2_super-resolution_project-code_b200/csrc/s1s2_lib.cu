@@ -226,9 +226,9 @@ const KernelInfo* kernel_table() {
         t[K_HPOOL256] = make_kernel<256, 64, 1, 8, MODE_POOL, 2, true>();
         t[K_HINC] = make_kernel<96, 16, 1, 9, MODE_STORE, 2, true, true, 4>();  // inc.0: 32-byte rows, resident weights, 4 staging buffers
         t[K_HC96IN] = make_kernel<192, 32, 1, 10, MODE_STORE, 2, true>();   // down1.0.0: Cin = 96 as three 32-channel chunks
-        t[K_PX_STORE] = make_px_kernel<64, 4, MODE_STORE>();            // conv1.0: pixels on N (see conv_px.cuh)
-        t[K_PX_HEAD] = make_px_kernel<64, 4, MODE_HEAD>();              // conv1.2 + outc + scheduler, K padded 96 -> 128 per tap
-        t[K_PX_HEAD32] = make_px_kernel<32, 8, MODE_HEAD>();            // same with exact 32-channel chunks (default)
+        t[K_PX_STORE] = make_px_kernel<64, 7, MODE_STORE>();            // conv1.0: pixels on N (see conv_px.cuh)
+        t[K_PX_HEAD] = make_px_kernel<64, 7, MODE_HEAD>();              // conv1.2 + outc + scheduler, K padded 96 -> 128 per tap
+        t[K_PX_HEAD32] = make_px_kernel<32, 10, MODE_HEAD>();            // same with exact 32-channel chunks (default)
         t[K_STORE256_1] = make_kernel<256, 64, 1, 3, MODE_STORE, 1>();   // single-CTA variants: A/B measurement only
         t[K_POOL256_1] = make_kernel<256, 64, 1, 4, MODE_POOL, 1>();     // (S1S2_SINGLE_CTA_256=1)
         t[K_HEAD] = make_kernel<96, 32, 3, 6, MODE_HEAD>();     // conv1.2 + outc + scheduler
@@ -315,7 +315,7 @@ int dmalloc(s1s2_handle* h, void** p, size_t bytes, std::string* err) {
 // conv_px_kernel: pixels (16 x 16 tile of one image) on N, weight rows on M.
 int build_px_params(s1s2_handle* h, Layer& L, const KernelInfo& k, EncodeTiledFn enc, std::string* err) {
     const int Hl = h->H >> L.level, Wl = h->W >> L.level;
-    if (Hl % 16 != 0 || Wl % 16 != 0 || L.cout > 128 || L.taps_w != 3) {
+    if (Hl % 16 != 0 || Wl % 8 != 0 || L.cout > 128 || L.taps_w != 3) {
         set_err(err, "layer %s: geometry does not fit the pixels-on-N kernel", L.name);
         return S1S2_ERR_INVALID;
     }
@@ -327,7 +327,7 @@ int build_px_params(s1s2_handle* h, Layer& L, const KernelInfo& k, EncodeTiledFn
                               static_cast<cuuint64_t>(h->nalloc)};
         cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.src_pitch) * 2, static_cast<cuuint64_t>(Wl) * L.src_pitch * 2,
                                  static_cast<cuuint64_t>(Hl) * Wl * L.src_pitch * 2};
-        cuuint32_t box[4] = {static_cast<cuuint32_t>(k.kbox), 16, 16, 1};
+        cuuint32_t box[4] = {static_cast<cuuint32_t>(k.kbox), kPxHaloW, kPxHaloH, 1};      // 8 x 32 tile + 1-pixel ring
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&p.tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(L.src), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -348,7 +348,7 @@ int build_px_params(s1s2_handle* h, Layer& L, const KernelInfo& k, EncodeTiledFn
                               static_cast<cuuint64_t>(h->nalloc)};
         cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.dst_pitch) * 2, static_cast<cuuint64_t>(Wl) * L.dst_pitch * 2,
                                  static_cast<cuuint64_t>(Hl) * Wl * L.dst_pitch * 2};
-        cuuint32_t box[4] = {32, 16, 8, 1};     // half a tile per store
+        cuuint32_t box[4] = {32, 8, 16, 1};     // half a tile (8 wide x 16 tall) per store
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&p.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, L.dst, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -475,7 +475,7 @@ int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, cudaS
     if (k.px) {
         p.B = B;
         p.amax_in = amax_in;
-        const int tiles = (p.W >> 4) * (p.H >> 4) * B;
+        const int tiles = (p.W >> 3) * ((p.H + 31) >> 5) * B;
         k.fn<<<tiles < h->num_sms ? tiles : h->num_sms, 256, k.smem, st>>>(p);
         CK(cudaGetLastError());
         ++h->launches;
