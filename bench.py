@@ -10,7 +10,7 @@ Patches are independent units: N GPUs = N x batch patches per step, no data-path
   value     patches/s with inputs resident in HBM (CUDA events, barrier + synchronize on both sides, max over ranks)
   e2e       the same through the host-buffer entry s1s2_sample_host (pinned host cond + noise in, image out)
   roofline  tensor-pipe roofline of the conv kernel family (every launch in the timed region is one instantiation of
-            conv_umma_kernel): algorithmic FLOPs (301 851 475 968 per patch per model call)
+            conv kernel family): algorithmic FLOPs (301 851 475 968 per patch per model call)
             / device time, against MEASURED_PEAKS.json's sustained bf16 figure; `layers` lists every launch of one
             model call timed with a CUDA event pair on the launching stream.
   cpu_baseline  oracle/ (a port of the reference's PyTorch sampler) timed on this box's host cores, bounded sample.
@@ -302,13 +302,16 @@ def main():
     peak_tf, _, peak_src = peaks()
     flop_step = FLOP_PER_CALL * N_CALLS * B                      # per GPU per step
     achieved = flop_step * args.steps / (ms / 1e3) / 1e12       # TFLOP/s per GPU over the timed region
-    roof = {"bound": "tensor", "kernel": "conv_umma_kernel<BLOCK_N,KBOX,BOXES,STAGES,MODE> (all 16 launches of a model "
-            "call; timed region = 50 model calls x steps, nothing else launches)", "achieved": achieved, "peak": peak_tf,
+    roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv family: conv_umma_kernel<...> (14 launches per model call) + "
+            "conv_px_kernel<...> (conv1.0, conv1.2+outc+scheduler); timed region = 50 model calls x steps, nothing else launches",
+            "achieved": achieved, "peak": peak_tf,
             "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src, "traffic": None,
             "flop_per_launch_avg": FLOP_PER_CALL * B / 16}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        roof["traffic"] = json.load(open(tp))
+    if os.path.exists(tp) and B == 64:           # ncu --set full capture of one model call at batch 64 (profiles/)
+        tj = json.load(open(tp))
+        roof["traffic"] = tj["dram_total_GB"] * 1e9 / 16                     # DRAM bytes per launch (mean of the 16)
+        roof["traffic_detail"] = {k: tj[k] for k in ("source", "per", "dram_read_GB", "dram_write_GB", "algorithmic_activation_GB")}
     if not args.no_layers and rank == 0:
         lt = model.profile_layers(dev, H, W, B, reps=3)
         fl = dict(layer_flops())
