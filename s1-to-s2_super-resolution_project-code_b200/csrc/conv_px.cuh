@@ -34,15 +34,22 @@ struct PxSmem {
     static constexpr int kHaloRing = kPxHaloSlots * kHaloSlot;
     static constexpr int kStage = kABox;                // the ring streams weight tiles only
     static constexpr int kSubBytes = 128 * 64;          // [128 pixels = half a tile][32 ch] fp16, 64B swizzle
-    static constexpr int kStaging = 3 * kSubBytes;
+    static constexpr int kStagingBuf = 3 * kSubBytes;
+    static constexpr int kStaging = 2 * kStagingBuf;    // one buffer per epilogue warpgroup
     static constexpr int kBias = 128 * 4;
     static constexpr int kBytes = 1024 + kHaloRing + STAGES * kStage + kStaging + kBias + 256;
     static_assert(STAGES >= 2 && STAGES <= 10, "weight ring depth");
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
+// 384 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 and 8-11 two epilogue
+// warpgroups.  The epilogue is the long pole of these layers (transposition through shared memory, and for the head a
+// second pass with global loads), so the two TMEM accumulators are drained by different warpgroups: group g owns
+// accumulator g, staging buffer g and named barrier 1+g and handles every other tile of the CTA.
+constexpr int kPxThreads = 384;
+
 template <int KBOX, int STAGES, int MODE>
-__global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_constant__ ConvParams p) {
     using L = PxSmem<KBOX, STAGES>;
     static_assert(MODE == MODE_STORE || MODE == MODE_HEAD, "conv_px_kernel modes");
     constexpr int kRowBytes = KBOX * 2;
@@ -53,9 +60,9 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* halo_ring = smem;
     uint8_t* stage_base = smem + L::kHaloRing;
-    uint8_t* sout = stage_base + STAGES * L::kStage;
-    float* sbias = reinterpret_cast<float*>(sout + L::kStaging);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sout + L::kStaging + L::kBias);
+    uint8_t* sout0 = stage_base + STAGES * L::kStage;
+    float* sbias = reinterpret_cast<float*>(sout0 + L::kStaging);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sout0 + L::kStaging + L::kBias);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -181,10 +188,14 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
     } else if (warp >= 4) {
         // ================================================================= epilogue
         const int q = warp & 3;                     // TMEM lane quadrant = 32 output channels
-        const int et = q * 32 + lane;               // epilogue thread index 0..127 (= output channel in pass 1)
-        int acc = 0;
+        const int grp = (warp - 4) >> 2;            // epilogue warpgroup = accumulator = staging buffer
+        const int et = q * 32 + lane;               // thread index 0..127 inside the group (= output channel in pass 1)
+        const int acc = grp;
         uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint8_t* sout = sout0 + grp * L::kStagingBuf;
+        const int bar_id = 1 + grp;
+        const bool issuer = (q == 0 && lane == 0);  // the group's TMA-store thread
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x) {
             const int tx = tile % tiles_x;
             const int ty = (tile / tiles_x) % tiles_y;
             const int n = tile / (tiles_x * tiles_y);
@@ -199,9 +210,26 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 if constexpr (MODE == MODE_STORE) {
-                    if (warp == 4 && lane == 0) bulk_wait_read0();   // the previous stores have read the staging
+                    if (issuer) bulk_wait_read0();                   // the group's previous stores have read the staging
                 }
-                named_bar_sync(1, 128);                              // (HEAD: the previous pass 2 is done)
+                named_bar_sync(bar_id, 128);                         // (HEAD: the previous pass 2 is done)
+                // HEAD: this thread's pixel of pass 2; its state values are requested now so the global-load latency
+                // hides behind pass 1
+                const int px2 = et;
+                const int x2 = (tx << 3) + (px2 & 7), y2 = (ty << 5) + half * 16 + (px2 >> 3);
+                const bool inside = y2 < p.H;                     // H % 32 == 16: the tile's lower half is outside the image
+                const size_t pix = static_cast<size_t>(y2) * p.W + x2;
+                float xt4[kHeadOut] = {0.f, 0.f, 0.f, 0.f}, z4[kHeadOut] = {0.f, 0.f, 0.f, 0.f};
+                if constexpr (MODE == MODE_HEAD) {
+                    if (inside && sc.kind != STEP_NONE) {
+#pragma unroll
+                        for (int k = 0; k < kHeadOut; ++k) {
+                            const size_t idx = (static_cast<size_t>(n) * kHeadOut + k) * plane + pix;
+                            xt4[k] = p.head.x_t[idx];
+                            if (sc.flags & STEP_FLAG_NOISE) z4[k] = p.head.noise[idx];
+                        }
+                    }
+                }
                 if (q < 3) {
                     // pass 1: this thread's channel, 128 pixels of the half tile -> staging[pixel][channel]
                     const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
@@ -228,19 +256,17 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
                 }
                 if constexpr (MODE == MODE_STORE) {
                     fence_proxy_async_smem();
-                    named_bar_sync(1, 128);
-                    if (warp == 4 && lane == 0) {
+                    named_bar_sync(bar_id, 128);
+                    if (issuer) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
                             tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, c * 32, tx << 3, (ty << 5) + half * 16, n);
                         bulk_commit();
                     }
                 } else {
-                    named_bar_sync(1, 128);                          // hidden half tile complete in shared memory
+                    named_bar_sync(bar_id, 128);                     // hidden half tile complete in shared memory
                     // pass 2: this thread's pixel: outc over the 96 hidden channels, scheduler update, writes
-                    const int px = et;
-                    const int x = (tx << 3) + (px & 7), y = (ty << 5) + half * 16 + (px >> 3);
-                    const bool inside = y < p.H;                 // H % 32 == 16: the tile's lower half is outside the image
+                    const int px = px2, x = x2, y = y2;
                     float o[kHeadOut];
 #pragma unroll
                     for (int k = 0; k < kHeadOut; ++k) o[k] = p.head.b[k] * s_dn;
@@ -263,7 +289,6 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
                             }
                         }
                     }
-                    const size_t pix = static_cast<size_t>(y) * p.W + x;
                     float res[kHeadOut];
                     if (inside) {
 #pragma unroll
@@ -273,7 +298,7 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
                         if (p.head.pred_out != nullptr) p.head.pred_out[idx] = pr;
                         res[k] = pr;
                         if (sc.kind != STEP_NONE) {
-                            const float xt = p.head.x_t[idx];
+                            const float xt = xt4[k];
                             float x0 = 0.f, e = pr, xn;
                             if (sc.kind == STEP_EPS_DDIM) {
                                 x0 = __fdiv_rn(__fsub_rn(xt, __fmul_rn(sc.c0, pr)), sc.c1);
@@ -284,7 +309,7 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
                             const bool ddpm = sc.kind == STEP_EPS_DDPM || sc.kind == STEP_V_DDPM;
                             if (ddpm) xn = __fmul_rn(sc.c2, __fsub_rn(xt, __fmul_rn(sc.c3, e)));
                             else      xn = __fadd_rn(__fmul_rn(sc.c2, x0), __fmul_rn(sc.c3, e));
-                            if (sc.flags & STEP_FLAG_NOISE) xn = __fadd_rn(xn, __fmul_rn(sc.c4, p.head.noise[idx]));
+                            if (sc.flags & STEP_FLAG_NOISE) xn = __fadd_rn(xn, __fmul_rn(sc.c4, z4[k]));
                             if (sc.flags & STEP_FLAG_FINAL) xn = fminf(fmaxf(ddpm ? xn : x0, 0.f), 1.f);
                             p.head.x_t[idx] = xn;
                             res[k] = xn;
@@ -316,11 +341,10 @@ __global__ void __launch_bounds__(256, 1) conv_px_kernel(const __grid_constant__
                     if (lane == 0) atomicMax(p.head.amax_out + n, mx);
                 }
             }
-            acc ^= 1;
-            if (acc == 0) acc_ph ^= 1;
+            acc_ph ^= 1;                            // this group's accumulator is used once per two tiles
         }
         if constexpr (MODE == MODE_STORE) {
-            if (warp == 4 && lane == 0) bulk_wait0();
+            if (issuer) bulk_wait0();
         }
     }
 

@@ -226,8 +226,8 @@ const KernelInfo* kernel_table() {
         t[K_HPOOL256] = make_kernel<256, 64, 1, 8, MODE_POOL, 2, true>();
         t[K_HINC] = make_kernel<96, 16, 1, 9, MODE_STORE, 2, true, true, 4>();  // inc.0: 32-byte rows, resident weights, 4 staging buffers
         t[K_HC96IN] = make_kernel<192, 32, 1, 10, MODE_STORE, 2, true>();   // down1.0.0: Cin = 96 as three 32-channel chunks
-        t[K_PX_STORE] = make_px_kernel<64, 7, MODE_STORE>();            // conv1.0: pixels on N (see conv_px.cuh)
-        t[K_PX_HEAD] = make_px_kernel<64, 7, MODE_HEAD>();              // conv1.2 + outc + scheduler, K padded 96 -> 128 per tap
+        t[K_PX_STORE] = make_px_kernel<64, 5, MODE_STORE>();            // conv1.0: pixels on N (see conv_px.cuh)
+        t[K_PX_HEAD] = make_px_kernel<64, 5, MODE_HEAD>();              // conv1.2 + outc + scheduler, K padded 96 -> 128 per tap
         t[K_PX_HEAD32] = make_px_kernel<32, 10, MODE_HEAD>();            // same with exact 32-channel chunks (default)
         t[K_STORE256_1] = make_kernel<256, 64, 1, 3, MODE_STORE, 1>();   // single-CTA variants: A/B measurement only
         t[K_POOL256_1] = make_kernel<256, 64, 1, 4, MODE_POOL, 1>();     // (S1S2_SINGLE_CTA_256=1)
@@ -476,7 +476,7 @@ int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, cudaS
         p.B = B;
         p.amax_in = amax_in;
         const int tiles = (p.W >> 3) * ((p.H + 31) >> 5) * B;
-        k.fn<<<tiles < h->num_sms ? tiles : h->num_sms, 256, k.smem, st>>>(p);
+        k.fn<<<tiles < h->num_sms ? tiles : h->num_sms, kPxThreads, k.smem, st>>>(p);
         CK(cudaGetLastError());
         ++h->launches;
         return S1S2_OK;
