@@ -91,14 +91,16 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
 }
 
 // Conv2d weight OIHW f32 -> [cout][tap][cin] fp16 (K-major rows for the UMMA B operand).
-__global__ void repack_conv3_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin) {
-    const size_t n = static_cast<size_t>(cout) * 9 * cin;
+// `cin_pad` >= cin: input channels past cin get zero weights (down1.0.0 reads 96 real + 32 always-zero channels so that
+// it runs as two 64-channel chunks).
+__global__ void repack_conv3_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin, int cin_pad) {
+    const size_t n = static_cast<size_t>(cout) * 9 * cin_pad;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int ci = static_cast<int>(i % cin);
-        const int tap = static_cast<int>((i / cin) % 9);
-        const int co = static_cast<int>(i / (static_cast<size_t>(cin) * 9));
-        out[i] = __float2half_rn(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap]);
+        const int ci = static_cast<int>(i % cin_pad);
+        const int tap = static_cast<int>((i / cin_pad) % 9);
+        const int co = static_cast<int>(i / (static_cast<size_t>(cin_pad) * 9));
+        out[i] = ci < cin ? __float2half_rn(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap]) : __float2half_rn(0.f);
     }
 }
 // inc.0.weight [cout][9][3][3] -> [cout][tap][16] in the pixel-record order of pack_input_kernel.
@@ -241,7 +243,8 @@ struct Layer {
     const char* name;        // state_dict prefix
     KernelId kid;
     int level;               // input resolution = (H >> level, W >> level)
-    int cin;                 // K per tap (padded for inc)
+    int cin;                 // K per tap (padded for inc and down1.0.0)
+    int cin_real = 0;        // input channels of the state_dict tensor when cin is padded (0: same as cin)
     int ntot;                // GEMM N (CONVT: 4 * cout)
     int cout;                // real output channels per pixel
     int taps_w;
@@ -587,7 +590,7 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     const size_t P0 = static_cast<size_t>(H) * W, P1 = P0 / 4, P2 = P0 / 16, P3 = P0 / 64;
     __half *cat1, *d1a, *cat2, *d2a, *cat3, *d3a, *e4, *c3a, *c3b, *c2a, *c2b, *c1a;
     struct { __half** p; size_t elems; } bufs[] = {
-        {&h->xin16, N * P0 * 16}, {&cat1, N * P0 * 192}, {&d1a, N * P0 * 192}, {&cat2, N * P1 * 384},
+        {&h->xin16, N * P0 * 16}, {&cat1, N * P0 * 224}, {&d1a, N * P0 * 192}, {&cat2, N * P1 * 384},
         {&d2a, N * P1 * 384},     {&cat3, N * P2 * 768}, {&d3a, N * P2 * 768}, {&e4, N * P3 * 768},
         {&c3a, N * P2 * 384},     {&c3b, N * P2 * 384},  {&c2a, N * P1 * 192}, {&c2b, N * P1 * 192},
         {&c1a, N * P0 * 96}};
@@ -625,8 +628,15 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
         h->layers.push_back(L);
     };
     //   name          kernel    lvl cin  N     cout taps src          pitch dst           pitch
-    add("inc.0",       K_INC,    0,  16,  96,   96,  3,   h->xin16,    16,   cat1 + 96,    192);
-    add("down1.0.0",   K_C96IN,  0,  96,  192,  192, 3,   cat1 + 96,   192,  d1a,          192);
+    // cat1 = [up1 (96) | inc (96) | 32 channels that stay zero]: down1.0.0 reads [inc | zeros] as Cin = 128 = two
+    // 64-channel chunks (zero weights on the padding) and so runs in halo mode like every other 3x3 layer.
+    add("inc.0",       K_INC,    0,  16,  96,   96,  3,   h->xin16,    16,   cat1 + 96,    224);
+    if (getenv("S1S2_NO_PAD96") == nullptr) {
+        add("down1.0.0", K_STORE,  0,  128, 192,  192, 3,   cat1 + 96,   224,  d1a,          192);
+        h->layers.back().cin_real = 96;
+    } else {                                   // A/B: exact K = 96 per tap as three 32-channel chunks, no halo
+        add("down1.0.0", K_C96IN,  0,  96,  192,  192, 3,   cat1 + 96,   224,  d1a,          192);
+    }
     add("down1.0.2",   K_POOL,   0,  192, 192,  192, 3,   d1a,         192,  cat2 + 192,   384);
     add("down2.0.0",   K_STORE,  1,  192, 384,  384, 3,   cat2 + 192,  384,  d2a,          384);
     add("down2.0.2",   K_POOL,   1,  384, 384,  384, 3,   d2a,         384,  cat3 + 384,   768);
@@ -638,8 +648,8 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     add("up2",         K_CONVT256, 2, 384, 768,  192, 1,  c3b,         384,  cat2,         384);
     add("conv2.0",     K_STORE,  1,  384, 192,  192, 3,   cat2,        384,  c2a,          192);
     add("conv2.2",     K_STORE,  1,  192, 192,  192, 3,   c2a,         192,  c2b,          192);
-    add("up1",         K_CONVT,  1,  192, 384,  96,  1,   c2b,         192,  cat1,         192);
-    add("conv1.0",     K_N96,    0,  192, 96,   96,  3,   cat1,        192,  c1a,          96);
+    add("up1",         K_CONVT,  1,  192, 384,  96,  1,   c2b,         192,  cat1,         224);
+    add("conv1.0",     K_N96,    0,  192, 96,   96,  3,   cat1,        224,  c1a,          96);
     add("conv1.2",     K_HEAD,   0,  96,  96,   96,  3,   c1a,         96,   nullptr,      0);
 
     if (getenv("S1S2_NO_HALO") == nullptr) {
@@ -677,11 +687,11 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
         if (rc != S1S2_OK) { s1s2_destroy(h); return rc; }
     }
     // views for s1s2_debug_activation: name = the oracle's tap key
-    h->views = {{"inc", cat1 + 96, 192, 96, 0},      {"down1.0", d1a, 192, 192, 0}, {"down1", cat2 + 192, 384, 192, 1},
+    h->views = {{"inc", cat1 + 96, 224, 96, 0},      {"down1.0", d1a, 192, 192, 0}, {"down1", cat2 + 192, 384, 192, 1},
                 {"down2.0", d2a, 384, 384, 1},       {"down2", cat3 + 384, 768, 384, 2}, {"down3.0", d3a, 768, 768, 2},
                 {"down3", e4, 768, 768, 3},          {"up3", cat3, 768, 384, 2},    {"conv3.0", c3a, 384, 384, 2},
                 {"conv3", c3b, 384, 384, 2},         {"up2", cat2, 384, 192, 1},    {"conv2.0", c2a, 192, 192, 1},
-                {"conv2", c2b, 192, 192, 1},         {"up1", cat1, 192, 96, 0},     {"conv1.0", c1a, 96, 96, 0},
+                {"conv2", c2b, 192, 192, 1},         {"up1", cat1, 224, 96, 0},     {"conv1.0", c1a, 96, 96, 0},
                 {"xin16", h->xin16, 16, 16, 0}};
     if (cudaDeviceSynchronize() != cudaSuccess) {
         set_err(err, "arena initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -740,10 +750,11 @@ int s1s2_load_weights(s1s2_handle* h, int n, const char* const* names, const flo
             repack_convt_kernel<<<512, 256, 0, st>>>(w, L.w, L.cin, L.cout);
             tile_bias_kernel<<<8, 256, 0, st>>>(b, L.bias, L.cout, 4);
         } else {
-            if ((rc = find(nm + ".weight", static_cast<int64_t>(L.cout) * L.cin * 9, &w)) ||
+            const int cin_real = L.cin_real > 0 ? L.cin_real : L.cin;
+            if ((rc = find(nm + ".weight", static_cast<int64_t>(L.cout) * cin_real * 9, &w)) ||
                 (rc = find(nm + ".bias", L.cout, &b)))
                 return rc;
-            repack_conv3_kernel<<<1024, 256, 0, st>>>(w, L.w, L.cout, L.cin);
+            repack_conv3_kernel<<<1024, 256, 0, st>>>(w, L.w, L.cout, cin_real, L.cin);
             tile_bias_kernel<<<8, 256, 0, st>>>(b, L.bias, L.cout, 1);
         }
         h->launches += 2;
