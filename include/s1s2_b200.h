@@ -102,11 +102,26 @@ int s1s2_sample_host(s1s2_handle* h, const s1s2_step* steps, int n_steps, const 
 int s1s2_tile_extract(int device, const float* scene, const uint8_t* vmask, int SH, int SW, const int32_t* origins,
                       int N, int ps, float* cond, uint8_t* mask, float* valid_ratio, void* stream);
 
+/* Patch.py's four window quality tests on the target (Patch.py:88-114,205-224) for the windows in `origins`.
+ *   scene f32[Ci,SH,SW], target f32[4,SH,SW] (B2,B3,B4,B8 reflectance), colloc u8[SH,SW] or NULL: device
+ *   thresholds[5] host: valid_ratio_threshold, variance_threshold, dark_thr, dark_max_ratio, texture_thr
+ *   stats f32[N,8] device out: valid_ratio, var[0..3], dark_fraction, laplacian_var, code (0 keep, 1..4 = failed test) */
+int s1s2_tile_filter(int device, const float* scene, int Ci, const float* target, const uint8_t* colloc, int SH, int SW,
+                     const int32_t* origins, int N, int ps, const float* thresholds, float* stats, void* stream);
+
 /* Uniform-weight overlap blend (not in the reference; definition in DESIGN.md): gather formulation, deterministic.
  *   preds f32[N,C,ps,ps] device; origins int32[N,2] device, sorted in Patch.py iteration order on a regular
  *   `stride` grid; canvas f32[C,SH,SW] and cover u8[SH,SW] device out. */
 int s1s2_stitch(int device, const float* preds, const int32_t* origins, int N, int C, int ps, int stride, int SH,
                 int SW, float* canvas, uint8_t* cover, void* stream);
+
+/* Evaluation metrics of N predicted patches in one pass each (the drivers' per-file metric calls:
+ * masked_mae / masked_mse / psnr / ssim_simple, Evaluation/DDIM_Multi-step.py:72-101; sam / ergas,
+ * Evaluation_Updated/Evaluation_Pure_Generation.py:229-254).
+ *   pred, gt f32[N,C,HW] device; mask u8[N,HW] device or NULL (all valid); C <= 8
+ *   out f64[N,8] device: mae, mse, psnr, ssim_simple, sam, ergas, valid-pixel count, 0 */
+int s1s2_patch_metrics(int device, const float* pred, const float* gt, const uint8_t* mask, int N, int C, int HW,
+                       double* out, void* stream);
 
 /* Per-layer parity tap: converts the named activation of the LAST model call (fp16 NHWC arena view) to float32
  * NCHW.  Names follow the network's blocks: "inc", "down1", "down2", "down3", "up3", "conv3", "up2", "conv2",

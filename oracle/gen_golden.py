@@ -216,6 +216,42 @@ def main():
     out["norm/origins"] = np.array(idx, np.int32); out["norm/ps_stride"] = np.array([ps, st], np.int32)
     np.savez_compressed(os.path.join(args.out, "patch.npz"), **out)
 
+    # ---------------------------------------------------------------- Patch.py quality filters (Patch.py:88-114,205-224)
+    out = {}
+    rng = np.random.default_rng(11)
+    Hh, Ww, ps, st = 96, 160, 32, 16
+    yy, xx = np.mgrid[0:Hh, 0:Ww].astype(np.float32)
+    base = 0.35 + 0.25 * np.sin(yy / 9.0) * np.cos(xx / 13.0)
+    target = np.stack([np.clip(base * s_ + rng.normal(0, 0.03, (Hh, Ww)), 0, 1) for s_ in (0.8, 0.9, 1.0, 1.3)]).astype(np.float32)
+    target[:, 0:48, 0:48] = 0.01 + rng.random((4, 48, 48)).astype(np.float32) * 0.08      # dark block (var > 1e-4)
+    target[:, 48:96, 96:160] = 0.4                                                          # flat block (var < 1e-4, no texture)
+    target[:, 0:48, 96:160] = (0.5 + 0.10 * np.sin(yy[0:48, 96:160] / 15.0)).astype(np.float32)     # smooth: varied but textureless
+    target[rng.random((4, Hh, Ww)) < 0.01] = np.nan
+    inputs = rng.normal(-12, 4, (4, Hh, Ww)).astype(np.float32)
+    inputs[:, 60:96, 0:30] = np.nan                                                        # low valid ratio windows
+    colloc = (rng.random((Hh, Ww)) > 0.03).astype(np.uint8)
+    M_all = pt.build_mask(inputs, target, colloc)
+    rows = []
+    import warnings
+    for (r, c) in pt.patch_iter(Hh, Ww, ps, st):
+        Y = target[:, r:r + ps, c:c + ps].copy(); M = M_all[r:r + ps, c:c + ps].copy()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            vr = float(M.mean())
+            var = [float(np.nanvar(Y[ch][M])) for ch in range(4)]
+            dk = float(pt.dark_fraction(Y, M, thr=0.10))
+            lv = float(pt.laplacian_var(Y[3], M))
+        code = 0                                                                           # Patch.py:205-224, default thresholds
+        if vr < 0.80: code = 1
+        elif all(v < 1e-4 for v in var): code = 2
+        elif dk > 0.60: code = 3
+        elif lv < 5e-5: code = 4
+        rows.append([r, c, code, vr] + var + [dk, lv])
+    out["filt/inputs"] = inputs; out["filt/target"] = target; out["filt/colloc"] = colloc
+    out["filt/mask"] = M_all.astype(np.uint8); out["filt/ps_stride"] = np.array([ps, st], np.int32)
+    out["filt/rows"] = np.array(rows, np.float64)      # row, col, code, valid_ratio, var0..3, dark_fraction, laplacian_var
+    np.savez_compressed(os.path.join(args.out, "filters.npz"), **out)
+
     for f in sorted(os.listdir(args.out)):
         print(f, os.path.getsize(os.path.join(args.out, f)))
 

@@ -81,6 +81,63 @@ def extract_all(inputs: np.ndarray, vmask: np.ndarray, ps: int, stride: int, val
             np.stack(masks) if n else np.zeros((0, ps, ps), np.uint8))
 
 
+# ---------------------------------------------------------------------------------------------- quality filters
+def band_variances(Y: np.ndarray, M: np.ndarray) -> np.ndarray:
+    """Per-band variance of the target over valid pixels (Patch.py:211-214 uses np.nanvar(Y[ch][M]))."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.array([np.nanvar(Y[ch][M]) for ch in range(Y.shape[0])], dtype=np.float64)
+
+
+def dark_fraction(Y: np.ndarray, M: np.ndarray, thr: float = 0.10) -> float:
+    """Patch.py:88-98: share of valid pixels with mean(B2,B3,B4) < thr and B8 < thr; 1.0 for an empty mask."""
+    if not M.any():
+        return 1.0
+    vis = (Y[0] + Y[1] + Y[2]) / 3.0
+    return float(((vis < thr) & (Y[3] < thr) & M).sum()) / float(M.sum())
+
+
+def laplacian_var(img: np.ndarray, M: np.ndarray) -> float:
+    """Patch.py:100-114: variance over valid pixels of the 5-point Laplacian with a symmetric patch boundary
+    (scipy.signal.convolve2d(mode="same", boundary="symm") restated with np.pad); NaN stencils are ignored (nanvar)."""
+    import warnings
+    a = img.astype(np.float32).copy()
+    bad = ~np.isfinite(a)
+    if (bad & M).any():
+        a[bad] = np.nanmean(a[M])
+    q = np.pad(a, 1, mode="symmetric")
+    with np.errstate(invalid="ignore"):
+        L = q[:-2, 1:-1] + q[2:, 1:-1] + q[1:-1, :-2] + q[1:-1, 2:] - 4.0 * q[1:-1, 1:-1]
+        # convolve2d multiplies the four corner samples by the kernel's zeros: a non-finite corner still poisons L
+        L = L + 0.0 * (q[:-2, :-2] + q[:-2, 2:] + q[2:, :-2] + q[2:, 2:])
+    if not M.any():
+        return 0.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return float(np.nanvar(L[M]))
+
+
+def filter_decision(Y, M, valid_ratio_threshold=0.80, variance_threshold=1e-4, dark_thr=0.10, dark_max_ratio=0.60,
+                    texture_thr=5e-5):
+    """The four tests of Patch.py:205-224 in order; returns (code, stats): code 0 = keep, 1 = valid ratio, 2 = flat
+    target, 3 = too dark, 4 = no texture; stats = (valid_ratio, var[0..C-1], dark_fraction, laplacian_var)."""
+    vr = float(M.mean()) if M.size else 0.0
+    var = band_variances(Y, M)
+    dk = dark_fraction(Y, M, dark_thr)
+    lv = laplacian_var(Y[3], M)
+    code = 0
+    if vr < valid_ratio_threshold:
+        code = 1
+    elif all(v < variance_threshold for v in var):
+        code = 2
+    elif dk > dark_max_ratio:
+        code = 3
+    elif lv < texture_thr:
+        code = 4
+    return code, (vr, var, dk, lv)
+
+
 def stitch(preds: np.ndarray, origins: np.ndarray, H: int, W: int):
     """Uniform-weight overlap blend.  preds f32[N,C,ps,ps], origins i32[N,2] -> (canvas f32[C,H,W], cover u8[H,W]).
 

@@ -1011,6 +1011,37 @@ int s1s2_tile_extract(int device, const float* scene, const uint8_t* vmask, int 
     return S1S2_OK;
 }
 
+int s1s2_tile_filter(int device, const float* scene, int Ci, const float* target, const uint8_t* colloc, int SH, int SW,
+                     const int32_t* origins, int N, int ps, const float* thresholds, float* stats, void* stream) {
+    std::string* err = &g_error;
+    if (N == 0) return S1S2_OK;
+    if (scene == nullptr || target == nullptr || origins == nullptr || thresholds == nullptr || stats == nullptr || N < 0 ||
+        Ci < 1 || ps < 1 || ps > SH || ps > SW) {
+        set_err(err, "s1s2_tile_filter: bad argument (N %d, Ci %d, ps %d, scene %d x %d)", N, Ci, ps, SH, SW);
+        return S1S2_ERR_INVALID;
+    }
+    CK(cudaSetDevice(device));
+    FilterThresholds th{thresholds[0], thresholds[1], thresholds[2], thresholds[3], thresholds[4]};
+    tile_filter_kernel<<<N, kFilterThreads, 0, static_cast<cudaStream_t>(stream)>>>(scene, Ci, target, colloc, SH, SW, origins, ps,
+                                                                                   th, stats);
+    CK(cudaGetLastError());
+    return S1S2_OK;
+}
+
+int s1s2_patch_metrics(int device, const float* pred, const float* gt, const uint8_t* mask, int N, int C, int HW,
+                       double* out, void* stream) {
+    std::string* err = &g_error;
+    if (N == 0) return S1S2_OK;
+    if (pred == nullptr || gt == nullptr || out == nullptr || N < 0 || C < 1 || C > kMetricsMaxC || HW < 1) {
+        set_err(err, "s1s2_patch_metrics: bad argument (N %d, C %d, HW %d)", N, C, HW);
+        return S1S2_ERR_INVALID;
+    }
+    CK(cudaSetDevice(device));
+    patch_metrics_kernel<<<N, kMetricsThreads, 0, static_cast<cudaStream_t>(stream)>>>(pred, gt, mask, C, HW, out);
+    CK(cudaGetLastError());
+    return S1S2_OK;
+}
+
 int s1s2_stitch(int device, const float* preds, const int32_t* origins, int N, int C, int ps, int stride, int SH, int SW,
                 float* canvas, uint8_t* cover, void* stream) {
     std::string* err = &g_error;

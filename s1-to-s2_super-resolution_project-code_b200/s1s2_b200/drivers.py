@@ -163,11 +163,11 @@ def cmd_true_infer(args):
                     noise.append(torch.randn((1, gt.size(1), gt.size(2), gt.size(3)), device=device))
                 x0 = samplers.ddpm_ddim_generate(model, cond, alpha_bar, t_start=args.t_start, steps=args.ddim_steps,
                                                  noise=torch.cat(noise, 0))
+                mk = None if any(m is None for m in mask) else torch.cat(mask, 0)
+                vals = metrics.patch_metrics(x0, gt, mk).cpu()        # one fused pass + one copy for the whole batch
                 for i in range(len(names)):
-                    p, g, m = x0[i:i + 1], gt[i:i + 1], mask[i]
-                    per[i]["mae"].append(metrics.masked_mae(p, g, m)); per[i]["mse"].append(metrics.masked_mse(p, g, m))
-                    per[i]["psnr"].append(metrics.psnr(p, g, m)); per[i]["sam"].append(metrics.sam(p, g, m))
-                    per[i]["ergas"].append(metrics.ergas(p, g, m))
+                    for k, col in (("mae", 0), ("mse", 1), ("psnr", 2), ("sam", 4), ("ergas", 5)):
+                        per[i][k].append(float(vals[i, col]))
             for i, fname in enumerate(names):
                 mu = {k: float(np.mean(v)) for k, v in per[i].items()}
                 sd = {k: float(np.std(v, ddof=0)) for k, v in per[i].items()}

@@ -1,9 +1,33 @@
 """Patch-level agreement metrics with the reference's definitions (product-side copy used by the sampler
 wrappers' return values and the drivers): masked_mae / masked_mse / psnr / ssim_simple
 (Evaluation/DDIM_Multi-step.py:72-101), sam / ergas (Evaluation_Updated/Evaluation_Pure_Generation.py:229-254)."""
+import ctypes as C
 import math
 
 import torch
+
+METRIC_NAMES = ("mae", "mse", "psnr", "ssim_simple", "sam", "ergas", "valid")
+
+
+def patch_metrics(pred, tgt, mask=None):
+    """All six metrics of N patches in one fused CUDA pass each (s1s2_patch_metrics): f64[N,7] in METRIC_NAMES order.
+    pred, tgt f32[N,C,H,W] on the same CUDA device; mask [N,H,W] / [N,1,H,W] (non-zero = valid) or None.
+    One device->host copy of the result replaces ~10 `.item()` synchronisations per patch of the reference drivers."""
+    from . import _lib
+    if pred.device.type != "cuda":
+        raise _lib.S1S2Error("patch_metrics runs on a CUDA device only (no CPU fallback)")
+    N, Cn, H, W = pred.shape
+    pred = pred.to(torch.float32).contiguous()
+    tgt = tgt.to(device=pred.device, dtype=torch.float32).contiguous()
+    m = None
+    if mask is not None:
+        m = (mask.to(pred.device).reshape(N, H * W) > 0).to(torch.uint8).contiguous()
+    out = torch.empty((N, 8), device=pred.device, dtype=torch.float64)
+    idx = pred.device.index if pred.device.index is not None else torch.cuda.current_device()
+    stream = torch.cuda.current_stream(pred.device).cuda_stream
+    _lib.check(_lib.lib().s1s2_patch_metrics(idx, pred.data_ptr(), tgt.data_ptr(), m.data_ptr() if m is not None else None,
+                                             N, Cn, H * W, out.data_ptr(), C.c_void_p(stream)))
+    return out[:, :7]
 
 
 def _weights(pred, mask):

@@ -64,6 +64,35 @@ def tile_extract(scene: torch.Tensor, origins, ps: int, vmask: torch.Tensor = No
     return cond, mask, ratio
 
 
+FILTER_CODES = ("keep", "valid_ratio", "variance", "dark", "texture")
+
+
+def tile_filter(scene: torch.Tensor, target: torch.Tensor, origins, ps: int, colloc: torch.Tensor = None,
+                valid_ratio_threshold=0.80, variance_threshold=1e-4, dark_thr=0.10, dark_max_ratio=0.60, texture_thr=5e-5):
+    """Patch.py's window filters (Patch.py:205-224, defaults :327-337) on the device: stats f32[N,8] =
+    valid_ratio, var[0..3], dark_fraction, laplacian_var, code (index into FILTER_CODES; 0 = the window is kept)."""
+    dev = scene.device
+    idx = _dev_index(scene)
+    scene = scene.to(torch.float32).contiguous()
+    target = target.to(device=dev, dtype=torch.float32).contiguous()
+    if target.ndim != 3 or target.shape[0] != 4 or target.shape[1:] != scene.shape[1:]:
+        raise ValueError(f"target must be f32[4,H,W] on the scene's grid, got {tuple(target.shape)}")
+    org = torch.as_tensor(np.ascontiguousarray(origins, dtype=np.int32)).reshape(-1, 2)
+    N = org.shape[0]
+    SH, SW = scene.shape[1:]
+    if N and (int(org.min()) < 0 or int(org[:, 0].max()) + ps > SH or int(org[:, 1].max()) + ps > SW):
+        raise ValueError("window outside the scene")
+    org_d = org.to(dev)
+    cl = colloc.to(device=dev, dtype=torch.uint8).contiguous() if colloc is not None else None
+    stats = torch.empty((N, 8), device=dev, dtype=torch.float32)
+    th = (C.c_float * 5)(valid_ratio_threshold, variance_threshold, dark_thr, dark_max_ratio, texture_thr)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(_lib.lib().s1s2_tile_filter(idx, scene.data_ptr(), scene.shape[0], target.data_ptr(),
+                                           cl.data_ptr() if cl is not None else None, SH, SW, org_d.data_ptr(), N, ps, th,
+                                           stats.data_ptr(), C.c_void_p(stream)))
+    return stats
+
+
 def stitch(preds: torch.Tensor, origins, ps: int, stride: int, SH: int, SW: int):
     """preds f32[N,C,ps,ps] (cuda) + origins on the stride grid -> (canvas f32[C,SH,SW], cover u8[SH,SW])."""
     dev = preds.device

@@ -370,3 +370,53 @@ def test_drivers_write_reference_outputs(env, tmp_path):
     a = list(__import__("csv").reader(open(odir / "f" / "ddim_sweep_summary.csv")))[1][:7]
     b = list(__import__("csv").reader(open(odir / "g" / "ddim_sweep_summary.csv")))[1][:7]
     assert a == b
+
+
+def test_fused_patch_metrics_match_oracle(env):
+    """s1s2_patch_metrics vs the oracle's (reference-pinned) metric definitions, incl. the golden vector the reference
+    itself produced; tolerance 2e-6 relative (different summation order, fp64 vs torch fp32 sums)."""
+    from s1s2_b200 import metrics
+    z = np.load(os.path.join(G, "samplers.npz"))
+    p, g, m = (torch.from_numpy(z[k]) for k in ("metrics/pred", "x_gt", "metrics/mask"))
+    got = metrics.patch_metrics(p.to(env["dev"]), g.to(env["dev"]), m.to(env["dev"])).cpu().numpy()[0]
+    want = z["metrics/vals"]                      # mae, mse, psnr, ssim_simple, sam, ergas from the reference's code
+    assert np.allclose(got[:6], want, rtol=5e-6, atol=1e-7), (got[:6], want)
+    gen = torch.Generator().manual_seed(17)
+    N, C, H, W = 5, 4, 64, 48
+    pred = torch.rand((N, C, H, W), generator=gen)
+    tgt = torch.rand((N, C, H, W), generator=gen)
+    mask = (torch.rand((N, H, W), generator=gen) > 0.2).float()
+    mask[3] = 1.0
+    got = metrics.patch_metrics(pred.to(env["dev"]), tgt.to(env["dev"]), mask.to(env["dev"])).cpu().numpy()
+    for i in range(N):
+        a, b, mk = pred[i:i + 1], tgt[i:i + 1], mask[i:i + 1]
+        want = [ometrics.masked_mae(a, b, mk), ometrics.masked_mse(a, b, mk), ometrics.psnr(a, b, mk),
+                ometrics.ssim_simple(a, b), ometrics.sam(a, b, mk), ometrics.ergas(a, b, mk)]
+        assert np.allclose(got[i, :6], want, rtol=5e-6, atol=1e-7), (i, got[i], want)
+        assert got[i, 6] == float(mk.sum())
+    nomask = metrics.patch_metrics(pred.to(env["dev"]), tgt.to(env["dev"])).cpu().numpy()
+    assert np.allclose(nomask[0, :2], [ometrics.masked_mae(pred[:1], tgt[:1]), ometrics.masked_mse(pred[:1], tgt[:1])], rtol=5e-6)
+    identical = metrics.patch_metrics(pred.to(env["dev"]), pred.to(env["dev"])).cpu().numpy()
+    assert identical[0, 2] == 99.0 and identical[0, 0] == 0.0          # psnr's mse <= 1e-12 branch
+
+
+def test_quality_filters_match_golden(env):
+    """s1s2_tile_filter vs values the reference's own Patch.py functions produced (tests/golden/filters.npz): decision
+    codes exact, statistics within 1e-4 relative (fp64 one-pass sums vs numpy float32 pairwise sums)."""
+    from s1s2_b200 import patch
+    z = np.load(os.path.join(G, "filters.npz"))
+    ps, st = (int(v) for v in z["filt/ps_stride"])
+    rows = z["filt/rows"]
+    org = rows[:, :2].astype(np.int32)
+    stats = patch.tile_filter(torch.from_numpy(z["filt/inputs"]).to(env["dev"]), torch.from_numpy(z["filt/target"]).to(env["dev"]),
+                              org, ps, colloc=torch.from_numpy(z["filt/colloc"]).to(env["dev"])).cpu().numpy()
+    assert np.array_equal(stats[:, 7].astype(int), rows[:, 2].astype(int))
+    assert set(stats[:, 7].astype(int)) == {0, 1, 2, 3, 4}
+    assert np.allclose(stats[:, 0], rows[:, 3], rtol=0, atol=1e-7)                      # valid ratio
+    assert np.allclose(stats[:, 1:5], rows[:, 4:8], rtol=1e-4, atol=1e-9)               # band variances
+    assert np.allclose(stats[:, 5], rows[:, 8], rtol=0, atol=1e-7)                      # dark fraction
+    assert np.allclose(stats[:, 6], rows[:, 9], rtol=1e-4, atol=1e-10)                  # Laplacian variance
+    # a window with no valid pixel: ratio 0, dark fraction 1, texture 0 (Patch.py:93-94,114), code 1
+    scene = torch.full((4, 40, 40), float("nan"))
+    s0 = patch.tile_filter(scene.to(env["dev"]), torch.rand(4, 40, 40).to(env["dev"]), np.array([[4, 4]], np.int32), 32).cpu().numpy()[0]
+    assert s0[0] == 0.0 and s0[5] == 1.0 and s0[6] == 0.0 and int(s0[7]) == 1
