@@ -43,7 +43,12 @@ enum {
 };
 enum {
     S1S2_STEP_FINAL = 1,     /* result = clamp(x0,0,1) (DDIM kinds) / clamp(x',0,1) (DDPM kinds) */
-    S1S2_STEP_NOISE = 2      /* add c4 * z, z taken from the step_noise argument */
+    S1S2_STEP_NOISE = 2,     /* add c4 * z, z taken from the step_noise argument */
+    S1S2_STEP_PHILOX = 4     /* add c4 * z, z ~ N(0,1) generated in the kernel: Philox4x32-10 keyed by the seed of
+                                s1s2_set_noise_seed, counter (pixel, patch_base + patch slot, noise_index).  Replaces the
+                                per-step torch.randn_like of Limitation_Test.py:222 / DDIM_Multi-step_v_Prediction.py:172
+                                when the caller supplies no z (a DDPM-1000 chain at batch 64 would need 64 GB of it);
+                                statistically, not bitwise, equivalent to the reference's generator */
 };
 
 /* One model call + scheduler update.  The host computes the coefficients exactly as the reference would
@@ -86,6 +91,10 @@ int s1s2_forward(s1s2_handle* h, const float* xt_and_cond, const int64_t* t_idx,
 int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond, const float* x_init,
                 float init_scale, const float* step_noise, float* out, float* tap_pred, float* tap_x, int B,
                 void* stream);
+
+/* Seed of the in-kernel noise (S1S2_STEP_PHILOX) and the global patch id of batch slot 0, so that a patch draws the
+ * same noise wherever it sits in a batch or on whichever GPU it lands. */
+int s1s2_set_noise_seed(s1s2_handle* h, uint64_t seed, uint32_t patch_base);
 
 /* Same as s1s2_sample with HOST buffers (pinned memory recommended): copies cond / x_init to the device, samples,
  * copies the result back and synchronises the stream.  This is the end-to-end entry a host-side caller of the

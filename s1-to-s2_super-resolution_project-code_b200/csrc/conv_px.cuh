@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
                             xt4[k] = p.head.x_t[idx];
                             if (sc.flags & STEP_FLAG_NOISE) z4[k] = p.head.noise[idx];
                         }
+                        if (sc.flags & STEP_FLAG_PHILOX) philox_normal4(p.head, static_cast<uint32_t>(pix), static_cast<uint32_t>(n), z4);
                     }
                 }
                 if (q < 3) {
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
                             const bool ddpm = sc.kind == STEP_EPS_DDPM || sc.kind == STEP_V_DDPM;
                             if (ddpm) xn = __fmul_rn(sc.c2, __fsub_rn(xt, __fmul_rn(sc.c3, e)));
                             else      xn = __fadd_rn(__fmul_rn(sc.c2, x0), __fmul_rn(sc.c3, e));
-                            if (sc.flags & STEP_FLAG_NOISE) xn = __fadd_rn(xn, __fmul_rn(sc.c4, z4[k]));
+                            if (sc.flags & (STEP_FLAG_NOISE | STEP_FLAG_PHILOX)) xn = __fadd_rn(xn, __fmul_rn(sc.c4, z4[k]));
                             if (sc.flags & STEP_FLAG_FINAL) xn = fminf(fmaxf(ddpm ? xn : x0, 0.f), 1.f);
                             p.head.x_t[idx] = xn;
                             res[k] = xn;

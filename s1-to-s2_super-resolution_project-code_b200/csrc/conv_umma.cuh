@@ -34,7 +34,7 @@ namespace s1s2 {
 enum : int { MODE_STORE = 0, MODE_POOL = 1, MODE_CONVT = 2, MODE_HEAD = 3 };
 
 enum : int { STEP_NONE = 0, STEP_EPS_DDIM = 1, STEP_V_DDIM = 2, STEP_EPS_DDPM = 3, STEP_V_DDPM = 4 };
-enum : int { STEP_FLAG_FINAL = 1, STEP_FLAG_NOISE = 2 };
+enum : int { STEP_FLAG_FINAL = 1, STEP_FLAG_NOISE = 2, STEP_FLAG_PHILOX = 4 };
 enum : int { LAYER_FLAG_FIRST = 1 };   // first layer: apply the range scale in the epilogue (inputs are unscaled)
 
 constexpr float kXSplit = 4096.f;      // x_t travels as an fp16 pair: x = kXSplit * hi + lo
@@ -63,6 +63,9 @@ struct HeadParams {
     const float* noise;           // f32 NCHW per-step z (nullable)
     __half* xin16;                // next call's input planes, NHWC16 fp16 (nullable)
     uint32_t* amax_out;           // [B] float bits of max|x_{next}| per patch (nullable)
+    uint32_t seed_lo, seed_hi;    // STEP_FLAG_PHILOX: Philox4x32-10 key
+    uint32_t noise_stream;        // ... counter word 2 (the step's noise index)
+    uint32_t patch_base;          // ... counter word 1 = patch_base + patch slot (global patch id of slot 0)
     StepCoef step;                // by value: kind == STEP_NONE for a plain forward
 };
 
@@ -99,6 +102,35 @@ struct Halo {                                                   // KBOX channels
     static constexpr int kBytes = kHaloW * kHaloH * KBOX * 2;   // 23040 at KBOX = 64
     static constexpr int kSlot = (kBytes + 1023) / 1024 * 1024; // 1024-aligned ring slot
 };
+
+// Counter-based normal noise for the stochastic samplers (DDPM ancestral steps, DDIM eta > 0) when the caller does not
+// supply z: Philox4x32-10 keyed by the chain seed, counter = (pixel, global patch id, step noise index, 0) -> four
+// uniforms -> two Box-Muller pairs = the four channels of one pixel.  Reproducible whatever the batch composition.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ void philox_normal4(const HeadParams& hp, uint32_t pixel, uint32_t patch_slot, float (&z)[4]) {
+    uint32_t u[4];
+    philox4x32_10(pixel, hp.patch_base + patch_slot, hp.noise_stream, 0u, hp.seed_lo, hp.seed_hi, u);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float a = (static_cast<float>(u[2 * i]) + 0.5f) * 2.3283064365386963e-10f;        // (0, 1)
+        const float b = (static_cast<float>(u[2 * i + 1]) + 0.5f) * 2.3283064365386963e-10f;
+        const float r = sqrtf(-2.f * __logf(a));
+        float sn, cs;
+        __sincosf(6.283185307179586f * b, &sn, &cs);
+        z[2 * i] = r * cs;
+        z[2 * i + 1] = r * sn;
+    }
+}
 
 template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, int SBUF = 1>
 struct ConvSmem {

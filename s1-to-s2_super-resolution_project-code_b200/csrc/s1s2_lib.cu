@@ -276,6 +276,8 @@ struct s1s2_handle {
     std::vector<Layer> layers;
     std::vector<View> views;
     __half* xin16 = nullptr;
+    uint64_t noise_seed = 0x5EED5EEDull;   // S1S2_STEP_PHILOX key and patch id of batch slot 0
+    uint32_t patch_base = 0;
     uint32_t* amax = nullptr;     // [2][max_batch] float bits of max|x_t| per patch, ping-pong across model calls
     float head_w[kHeadOut * kHeadIn];
     float head_b[kHeadOut];
@@ -507,6 +509,8 @@ int run_network(s1s2_handle* h, int B, const HeadParams& head_io, const uint32_t
             hp.x_t = head_io.x_t;
             hp.pred_out = head_io.pred_out;
             hp.noise = head_io.noise;
+            hp.seed_lo = head_io.seed_lo; hp.seed_hi = head_io.seed_hi;
+            hp.noise_stream = head_io.noise_stream; hp.patch_base = head_io.patch_base;
             hp.xin16 = head_io.xin16;
             hp.amax_out = head_io.amax_out;
             hp.step = head_io.step;
@@ -820,6 +824,11 @@ int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float
             set_err(err, "step %d asks for noise but step_noise is NULL / noise_index < 0", i);
             return S1S2_ERR_INVALID;
         }
+        if ((steps[i].flags & S1S2_STEP_PHILOX) && ((steps[i].flags & S1S2_STEP_NOISE) || steps[i].noise_index < 0 ||
+                                                    !kernel_table()[h->layers.back().kid].px)) {
+            set_err(err, "step %d: in-kernel noise needs noise_index >= 0, no S1S2_STEP_NOISE, and the default head kernel", i);
+            return S1S2_ERR_INVALID;
+        }
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
@@ -842,6 +851,10 @@ int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float
         io.x_t = out;
         io.pred_out = tap_pred != nullptr ? tap_pred + static_cast<size_t>(i) * img : nullptr;
         io.noise = (steps[i].flags & S1S2_STEP_NOISE) ? step_noise + static_cast<size_t>(steps[i].noise_index) * img : nullptr;
+        io.seed_lo = static_cast<uint32_t>(h->noise_seed);
+        io.seed_hi = static_cast<uint32_t>(h->noise_seed >> 32);
+        io.noise_stream = static_cast<uint32_t>(steps[i].noise_index < 0 ? 0 : steps[i].noise_index);
+        io.patch_base = h->patch_base;
         io.xin16 = h->xin16;
         io.step.c0 = steps[i].c0;
         io.step.c1 = steps[i].c1;
@@ -856,6 +869,13 @@ int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float
         if (tap_x != nullptr)
             CK(cudaMemcpyAsync(tap_x + static_cast<size_t>(i) * img, out, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
+    return S1S2_OK;
+}
+
+int s1s2_set_noise_seed(s1s2_handle* h, uint64_t seed, uint32_t patch_base) {
+    if (h == nullptr) return S1S2_ERR_INVALID;
+    h->noise_seed = seed;
+    h->patch_base = patch_base;
     return S1S2_OK;
 }
 

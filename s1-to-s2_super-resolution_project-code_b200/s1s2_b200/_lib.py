@@ -9,7 +9,7 @@ from ._build import LIB_PATH
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE = 0, 1, 2, 3
 STEP_NONE, STEP_EPS_DDIM, STEP_V_DDIM, STEP_EPS_DDPM, STEP_V_DDPM = 0, 1, 2, 3, 4
-STEP_FINAL, STEP_NOISE = 1, 2
+STEP_FINAL, STEP_NOISE, STEP_PHILOX = 1, 2, 4
 
 
 class Step(C.Structure):
@@ -37,6 +37,7 @@ SIGNATURES = {
     "s1s2_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "s1s2_sample": (C.c_int, [C.c_void_p, C.POINTER(Step), C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "s1s2_set_noise_seed": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32]),
     "s1s2_sample_host": (C.c_int, [C.c_void_p, C.POINTER(Step), C.c_int, C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_void_p, C.c_int, C.c_void_p]),
     "s1s2_debug_activation": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int),

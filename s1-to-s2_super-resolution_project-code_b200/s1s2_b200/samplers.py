@@ -3,7 +3,9 @@
 Same names, argument order and return values as the reference functions; every function additionally accepts
 ``noise=`` (the initial unit-normal draw; drawn with ``torch.randn`` on the input's device when omitted, like the
 reference) and, for the stochastic samplers, ``step_noise=`` (f32[n,B,C,H,W], one slice per noisy step in
-execution order).  One library call enqueues the whole loop: no per-step host synchronisation, no torch ops.
+execution order).  Without ``step_noise`` the per-step noise is generated inside the last kernel of each model call
+(Philox4x32-10, ``seed=``; drawn from torch's generator when omitted): a DDPM-1000 chain at batch 64 would otherwise
+need 64 GB of pre-drawn z.  One library call enqueues the whole loop: no per-step host synchronisation, no torch ops.
 
   ddpm_ddim_generate     Evaluation_Updated/Evaluation_Pure_Generation.py:277-292
   ddim_multistep_eval    Evaluation/DDIM_Multi-step.py:116-137
@@ -29,7 +31,8 @@ def _f32c(t, dev):
     return t.to(device=dev, dtype=torch.float32).contiguous()
 
 
-def run_steps(model: UNetSmallB200, steps, cond, x_init, init_scale=1.0, step_noise=None, tap_pred=False, tap_x=False):
+def run_steps(model: UNetSmallB200, steps, cond, x_init, init_scale=1.0, step_noise=None, tap_pred=False, tap_x=False,
+              seed=None, patch_base=0):
     """Enqueue one sampling loop (list of _lib.Step) on the current stream.
 
     Returns the result tensor f32[B,C,H,W] (valid when the stream drains), or (result, taps) when taps are asked
@@ -58,6 +61,10 @@ def run_steps(model: UNetSmallB200, steps, cond, x_init, init_scale=1.0, step_no
         taps["pred"] = torch.empty((n,) + tuple(x_init.shape), device=dev, dtype=torch.float32)
     if tap_x:
         taps["x"] = torch.empty((n,) + tuple(x_init.shape), device=dev, dtype=torch.float32)
+    if any(s.flags & _lib.STEP_PHILOX for s in steps):      # in-kernel noise: key it (drawn from torch's generator if not given)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        _lib.check(_lib.lib().s1s2_set_noise_seed(eng.h, C.c_uint64(int(seed)), C.c_uint32(int(patch_base))), eng.h)
     stream = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(_lib.lib().s1s2_sample(eng.h, arr, n, _ptr(cond), _ptr(x_init), float(init_scale),
                                       _ptr(step_noise) if n_noise else None, _ptr(out), _ptr(taps.get("pred")),
@@ -129,14 +136,14 @@ def one_step_recon(model, x_gt, x_cond, alpha_bar, mask, t_small, rng_seed=None,
 # ---------------------------------------------------------------------------------------------- v, grid B
 @torch.no_grad()
 def ddim_multistep_eval_v(model, x_gt, x_cond, alpha_bar, mask, t_start=200, steps=20, eta: float = 0.0, noise=None,
-                          step_noise=None):
+                          step_noise=None, seed=None):
     T = len(alpha_bar)
     t_start = max(1, min(int(t_start), T - 1))
     idxs = schedule.grid_b(t_start, steps)
     ab = schedule._abar_cpu(alpha_bar)
-    x0 = run_steps(model, schedule.steps_grid_b(alpha_bar, idxs, "v", eta=float(eta)), x_cond,
+    x0 = run_steps(model, schedule.steps_grid_b(alpha_bar, idxs, "v", eta=float(eta), philox=step_noise is None), x_cond,
                    _randn(x_gt.shape, x_gt.device, noise), init_scale=float(torch.sqrt(1 - ab[t_start])),
-                   step_noise=step_noise)
+                   step_noise=step_noise, seed=seed)
     return masked_mae(x0, x_gt, mask), masked_mse(x0, x_gt, mask), x0
 
 
@@ -160,15 +167,15 @@ def one_step_recon_v(model, x_gt, x_cond, alpha_bar, mask, t_small, rng_seed=Non
 
 
 @torch.no_grad()
-def sample_ddim_v(model, cond, alpha_bar, C_tgt, steps=250, eta=0.05, t_start=None, noise=None, step_noise=None):
+def sample_ddim_v(model, cond, alpha_bar, C_tgt, steps=250, eta=0.05, t_start=None, noise=None, step_noise=None, seed=None):
     T = len(alpha_bar)
     B, _, H, W = cond.shape
     K = T - 1 if t_start is None else int(max(1, min(int(t_start), T - 1)))
     ab = schedule._abar_cpu(alpha_bar)
     idxs = schedule.grid_b(K, steps)
-    return run_steps(model, schedule.steps_grid_b(alpha_bar, idxs, "v", eta=float(eta)), cond,
+    return run_steps(model, schedule.steps_grid_b(alpha_bar, idxs, "v", eta=float(eta), philox=step_noise is None), cond,
                      _randn((B, C_tgt, H, W), cond.device, noise), init_scale=float(torch.sqrt(1 - ab[K])),
-                     step_noise=step_noise)
+                     step_noise=step_noise, seed=seed)
 
 
 # ---------------------------------------------------------------------------------------------- eps, grid B / DDPM
@@ -181,17 +188,17 @@ def ddim_sample(model, cond, alphas, alpha_bar, C_tgt, steps=50, noise=None):
 
 
 @torch.no_grad()
-def ddpm_sample(model, cond, betas, alphas, alpha_bar, C_tgt, noise=None, step_noise=None, t_list=None):
+def ddpm_sample(model, cond, betas, alphas, alpha_bar, C_tgt, noise=None, step_noise=None, t_list=None, seed=None):
     B, _, H, W = cond.shape
-    return run_steps(model, schedule.steps_ddpm(betas, alphas, alpha_bar, "eps", t_list), cond,
-                     _randn((B, C_tgt, H, W), cond.device, noise), step_noise=step_noise)
+    return run_steps(model, schedule.steps_ddpm(betas, alphas, alpha_bar, "eps", t_list, philox=step_noise is None), cond,
+                     _randn((B, C_tgt, H, W), cond.device, noise), step_noise=step_noise, seed=seed)
 
 
 @torch.no_grad()
-def sample_ddpm_v(model, cond, betas, alphas, alpha_bar, C_tgt, noise=None, step_noise=None, t_list=None):
+def sample_ddpm_v(model, cond, betas, alphas, alpha_bar, C_tgt, noise=None, step_noise=None, t_list=None, seed=None):
     B, _, H, W = cond.shape
-    return run_steps(model, schedule.steps_ddpm(betas, alphas, alpha_bar, "v", t_list), cond,
-                     _randn((B, C_tgt, H, W), cond.device, noise), step_noise=step_noise)
+    return run_steps(model, schedule.steps_ddpm(betas, alphas, alpha_bar, "v", t_list, philox=step_noise is None), cond,
+                     _randn((B, C_tgt, H, W), cond.device, noise), step_noise=step_noise, seed=seed)
 
 
 @torch.no_grad()

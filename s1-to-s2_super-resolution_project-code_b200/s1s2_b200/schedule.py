@@ -76,10 +76,11 @@ def steps_eps_grid_a(alpha_bar, t_start: int, steps: int):
     return out
 
 
-def steps_grid_b(alpha_bar, idxs, param: str, eta: float = 0.0, stochastic_form: bool = False):
+def steps_grid_b(alpha_bar, idxs, param: str, eta: float = 0.0, stochastic_form: bool = False, philox: bool = False):
     """ddim_sample (eps) / ddim_multistep_eval_v / sample_ddim_v (v): descending walk over idxs, last call at
     idxs[0] returns clamp(x0).  With eta > 0 (or stochastic_form) every non-final step adds sigma * z where
-    z = step_noise[k], k counting the non-final steps in execution order."""
+    z = step_noise[k], k counting the non-final steps in execution order (philox=True: z is generated in the kernel,
+    k is its Philox stream index)."""
     ab = _abar_cpu(alpha_bar)
     kind = _lib.STEP_EPS_DDIM if param == "eps" else _lib.STEP_V_DDIM
     out, k = [], 0
@@ -99,12 +100,13 @@ def steps_grid_b(alpha_bar, idxs, param: str, eta: float = 0.0, stochastic_form:
         else:
             sigma = eta * torch.sqrt((1 - a_prev) / (1 - a_t + 1e-8) * (1 - a_t / a_prev).clamp_min(0))
             dirc = torch.sqrt((1 - a_prev) - sigma ** 2).clamp_min(0)
-            out.append(_lib.Step(t, kind, _lib.STEP_NOISE, k, c0, c1, _f(torch.sqrt(a_prev)), _f(dirc), _f(sigma)))
+            out.append(_lib.Step(t, kind, _lib.STEP_PHILOX if philox else _lib.STEP_NOISE, k, c0, c1,
+                                 _f(torch.sqrt(a_prev)), _f(dirc), _f(sigma)))
             k += 1
     return out
 
 
-def steps_ddpm(betas, alphas, alpha_bar, param: str, t_list=None):
+def steps_ddpm(betas, alphas, alpha_bar, param: str, t_list=None, philox: bool = False):
     """ddpm_sample / sample_ddpm_v: ancestral chain over t_list (default T-1..0); z for step t>0 is
     step_noise[k], k counting in execution order; result = clamp(x after the last step)."""
     b, a, ab = (x.detach().to("cpu", torch.float32) for x in (betas, alphas, alpha_bar))
@@ -112,7 +114,7 @@ def steps_ddpm(betas, alphas, alpha_bar, param: str, t_list=None):
     kind = _lib.STEP_EPS_DDPM if param == "eps" else _lib.STEP_V_DDPM
     out, k = [], 0
     for n, t in enumerate(ts):
-        flags = (_lib.STEP_FINAL if n == len(ts) - 1 else 0) | (_lib.STEP_NOISE if t > 0 else 0)
+        flags = (_lib.STEP_FINAL if n == len(ts) - 1 else 0) | ((_lib.STEP_PHILOX if philox else _lib.STEP_NOISE) if t > 0 else 0)
         c0, c1 = (_f(torch.sqrt(ab[t])), _f(torch.sqrt(1.0 - ab[t]))) if param == "v" else (0.0, 0.0)
         out.append(_lib.Step(t, kind, flags, k if t > 0 else -1, c0, c1, _f(1 / torch.sqrt(a[t])),
                              _f(b[t] / torch.sqrt(1 - ab[t] + 1e-8)), _f(torch.sqrt(b[t]))))

@@ -420,3 +420,39 @@ def test_quality_filters_match_golden(env):
     scene = torch.full((4, 40, 40), float("nan"))
     s0 = patch.tile_filter(scene.to(env["dev"]), torch.rand(4, 40, 40).to(env["dev"]), np.array([[4, 4]], np.int32), 32).cpu().numpy()[0]
     assert s0[0] == 0.0 and s0[5] == 1.0 and s0[6] == 0.0 and int(s0[7]) == 1
+
+
+def test_in_kernel_philox_noise(env):
+    """S1S2_STEP_PHILOX: the z of a stochastic step generated inside the head kernel.  A DDPM step with c2 = 0, c4 = 1
+    returns z itself: unit-normal statistics, determined by (seed, patch id, step index, pixel) only - independent of the
+    batch a patch sits in - and different for different seeds / steps.  Parity with the reference's torch generator is
+    statistical by construction."""
+    from s1s2_b200 import _lib, samplers, schedule
+    B, H, W = 2, 64, 64
+    x, cond = _inputs(B, H, W, seed=61)
+    st = [_lib.Step(500, _lib.STEP_EPS_DDPM, _lib.STEP_PHILOX, 0, 0.0, 0.0, 0.0, 0.0, 1.0),
+          _lib.Step(400, _lib.STEP_EPS_DDPM, _lib.STEP_PHILOX, 1, 0.0, 0.0, 0.0, 0.0, 1.0)]
+    dev = env["dev"]
+    _, taps = samplers.run_steps(env["model"], st, cond.to(dev), x.to(dev), tap_x=True, seed=1234)
+    z = taps["x"].cpu()                                     # [2 steps, B, 4, H, W]
+    n = z[0].numel()
+    assert abs(float(z.mean())) < 4.0 / (2 * n) ** 0.5 and abs(float(z.var()) - 1.0) < 0.03
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.25         # kurtosis of a normal
+    assert float(z.abs().max()) < 6.5 and torch.isfinite(z).all()
+    assert abs(float((z[0] * z[1]).mean())) < 0.02          # steps are independent streams
+    assert abs(float((z[0, 0] * z[0, 1]).mean())) < 0.03    # patches are independent streams
+    for c in range(3):
+        assert abs(float((z[0, :, c] * z[0, :, c + 1]).mean())) < 0.03      # channels (Box-Muller pairs) uncorrelated
+    _, taps2 = samplers.run_steps(env["model"], st, cond.to(dev), x.to(dev), tap_x=True, seed=1234)
+    assert torch.equal(taps2["x"].cpu(), z)                 # same seed, same noise
+    _, taps3 = samplers.run_steps(env["model"], st, cond.to(dev), x.to(dev), tap_x=True, seed=99)
+    assert not torch.equal(taps3["x"].cpu(), z)
+    # patch 1 alone with patch_base = 1 draws what it drew as slot 1 of the batch
+    _, taps4 = samplers.run_steps(env["model"], st, cond[1:2].to(dev), x[1:2].to(dev), tap_x=True, seed=1234, patch_base=1)
+    assert torch.equal(taps4["x"].cpu()[:, 0], z[:, 1])
+    # a whole ancestral chain without supplied noise runs on it and stays in range
+    b16 = osched.cosine_betas(16)
+    y = samplers.ddpm_sample(env["model"], cond.to(dev), b16, 1 - b16, torch.cumprod(1 - b16, 0), 4, noise=x.to(dev), seed=5)
+    assert torch.isfinite(y).all() and float(y.min()) >= 0.0 and float(y.max()) <= 1.0
+    y2 = samplers.ddpm_sample(env["model"], cond.to(dev), b16, 1 - b16, torch.cumprod(1 - b16, 0), 4, noise=x.to(dev), seed=5)
+    assert torch.equal(y, y2)
