@@ -5,7 +5,7 @@ Python mirror of the reference's call pattern over the C ABI of libs1s2_b200.so 
 ``patch`` holds Patch.py's tiling plus the stitch; ``scene`` shards whole scenes across GPUs.
 There is no CPU / PyTorch fallback anywhere in this package.
 """
-from . import _lib, schedule, metrics, patch, samplers, scene  # noqa: F401
+from . import _lib, schedule, metrics, patch, patchio, samplers, scene  # noqa: F401
 from ._lib import S1S2Error  # noqa: F401
 from .model import UNetSmallB200  # noqa: F401
 from .schedule import cosine_beta_schedule, linear_beta_schedule, make_schedule  # noqa: F401

@@ -456,3 +456,39 @@ def test_in_kernel_philox_noise(env):
     assert torch.isfinite(y).all() and float(y.min()) >= 0.0 and float(y.max()) <= 1.0
     y2 = samplers.ddpm_sample(env["model"], cond.to(dev), b16, 1 - b16, torch.cumprod(1 - b16, 0), 4, noise=x.to(dev), seed=5)
     assert torch.equal(y, y2)
+
+
+def test_patch_files_match_patch_py_format(env, tmp_path):
+    """patchio.write_patches: the .npz files Patch.py would write (keys, dtypes, order, filter decisions, contents) from
+    in-memory rasters, checked against the oracle's restatement window by window; the drivers read them back."""
+    from s1s2_b200 import drivers, patchio
+    z = np.load(os.path.join(G, "filters.npz"))
+    ps, st = (int(v) for v in z["filt/ps_stride"])
+    inputs, target, colloc = z["filt/inputs"], z["filt/target"], z["filt/colloc"]
+    dev = env["dev"]
+    entries, counters = patchio.write_patches(torch.from_numpy(inputs).to(dev), torch.from_numpy(target).to(dev), str(tmp_path),
+                                              patch_size=ps, stride=st, colloc=torch.from_numpy(colloc).to(dev), folder="S1S2_x")
+    rows = z["filt/rows"]
+    codes = rows[:, 2].astype(int)
+    assert counters == dict(validratio_skipped=int((codes == 1).sum()), var_skipped=int((codes == 2).sum()),
+                            dark_skipped=int((codes == 3).sum()), texture_skipped=int((codes == 4).sum()))
+    kept = rows[codes == 0]
+    assert len(entries) == len(kept)
+    M_all = opatch.valid_mask(inputs, target, colloc)
+    for k, e in enumerate(entries):
+        d = np.load(os.path.join(tmp_path, e["npz"]))
+        assert set(d.files) == {"inputs", "target", "mask", "folder", "row", "col", "transform", "crs", "patch_size", "stride",
+                                "valid_ratio"}
+        r, c = int(kept[k, 0]), int(kept[k, 1])
+        assert (int(d["row"]), int(d["col"]), int(d["patch_size"]), int(d["stride"])) == (r, c, ps, st)
+        X, M, vr = opatch.extract_patch(inputs, M_all, r, c, ps)
+        assert d["mask"].dtype == np.uint8 and np.array_equal(d["mask"], M)
+        assert d["inputs"].dtype == np.float32 and np.abs(d["inputs"] - X).max() <= 2e-6
+        Y = target[:, r:r + ps, c:c + ps].copy()
+        Y[:, ~M.astype(bool)] = 0.0
+        assert np.array_equal(d["target"], np.nan_to_num(Y).astype(np.float32))
+        assert abs(float(d["valid_ratio"]) - vr) <= 1e-7
+    doc = patchio.write_manifest(str(tmp_path), entries, counters, patch_size=ps, stride=st)
+    assert doc["total_patches"] == len(kept) and doc["patches"][0]["patch_id"] == "000000"
+    x_cond, x_gt, mask, Cc, Ct = drivers.load_npz_as_tensors(os.path.join(tmp_path, entries[0]["npz"]), dev)
+    assert (Cc, Ct) == (4, 4) and tuple(x_cond.shape) == (1, 4, ps, ps) and mask is not None
