@@ -124,9 +124,11 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on an mbarrier given by a shared::cluster address (own or peer CTA)
+// arrive on an mbarrier given by a shared::cluster address (own or peer CTA).  Default semantics (release at CTA
+// scope): what is being published is "this warp has drained its TMEM lanes", already ordered by
+// tcgen05.fence::before_thread_sync; a cluster-scope release costs a MEMBAR.ALL.GPU + ERRBAR per warp per tile.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in the executing CTA's shared memory, the transaction bytes are credited to
 // the mbarrier at `bar_cluster_addr` (the leader CTA's barrier).
