@@ -57,7 +57,9 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
     constexpr uint32_t kIdesc = umma_idesc_f16(128, 256);
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer + offset (an integer round trip would lose the shared address space and turn every
+    // staging store / load into a generic ST.E / LD.E)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* halo_ring = smem;
     uint8_t* stage_base = smem + L::kHaloRing;
     uint8_t* sout0 = stage_base + STAGES * L::kStage;
@@ -245,8 +247,10 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const int px = j * 32 + i;
-                            const float v = fminf(fmaxf(__uint_as_float(r[i]) + b, 0.f), 65504.f);
-                            *reinterpret_cast<__half*>(sub + px * 64 + ((cchunk ^ ((px >> 1) & 3)) << 4)) = __float2half_rn(v);
+                            const float v = fmaxf(__uint_as_float(r[i]) + b, 0.f);
+                            uint16_t hv;
+                            asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hv) : "f"(v));
+                            *reinterpret_cast<uint16_t*>(sub + px * 64 + ((cchunk ^ ((px >> 1) & 3)) << 4)) = hv;
                         }
                     }
                 }

@@ -152,11 +152,11 @@ struct ConvSmem {
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
+// {lo: a, hi: b} as fp16 with round-to-nearest and saturation to +-65504 in ONE instruction
 __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
     __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
@@ -194,7 +194,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     constexpr uint32_t kIdesc = umma_idesc_f16(128 * CTAS, BLOCK_N);
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer + offset (an integer round trip would lose the shared address space and turn every
+    // staging store / load into a generic ST.E / LD.E)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_ring = smem;                       // halo mode: kHaloSlots activation halo tiles
     uint8_t* stage_base = smem + L::kARing;
     uint8_t* sout0 = stage_base + STAGES * L::kStage;
