@@ -24,21 +24,25 @@
 
 namespace s1s2 {
 
-constexpr int kPxHaloW = 10, kPxHaloH = 34, kPxHaloSlots = 2;
+constexpr int kPxHaloW = 10, kPxHaloH = 34;
 
-template <int KBOX, int STAGES>
+// TPS: weight tiles (taps) per ring stage, HSLOTS: halo ring depth (see conv_umma_kernel's TPS note: the issue loop is
+// ~300 cycles per stage, so KBOX = 32 stages of one tap = two MMAs were issue-bound).
+template <int KBOX, int STAGES, int TPS = 1, int HSLOTS = 2>
 struct PxSmem {
     static constexpr int kABox = 128 * KBOX * 2;        // weights: 128 rows (cout, zero-padded past the real rows)
     static constexpr int kHaloBytes = kPxHaloW * kPxHaloH * KBOX * 2;          // pixels: 8 x 32 tile + 1-pixel ring
     static constexpr int kHaloSlot = (kHaloBytes + 1023) / 1024 * 1024;
-    static constexpr int kHaloRing = kPxHaloSlots * kHaloSlot;
-    static constexpr int kStage = kABox;                // the ring streams weight tiles only
+    static constexpr int kHaloRing = HSLOTS * kHaloSlot;
+    static constexpr int kStage = TPS * kABox;          // the ring streams weight tiles only
     static constexpr int kSubBytes = 128 * 64;          // [128 pixels = half a tile][32 ch] fp16, 64B swizzle
     static constexpr int kStagingBuf = 3 * kSubBytes;
     static constexpr int kStaging = 2 * kStagingBuf;    // one buffer per epilogue warpgroup
     static constexpr int kBias = 128 * 4;
     static constexpr int kBytes = 1024 + kHaloRing + STAGES * kStage + kStaging + kBias + 256;
     static_assert(STAGES >= 2 && STAGES <= 10, "weight ring depth");
+    static_assert(TPS == 1 || TPS == 3, "taps per stage");
+    static_assert(HSLOTS == 2 || HSLOTS == 3, "halo ring depth");
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
@@ -48,9 +52,10 @@ struct PxSmem {
 // accumulator g, staging buffer g and named barrier 1+g and handles every other tile of the CTA.
 constexpr int kPxThreads = 384;
 
-template <int KBOX, int STAGES, int MODE>
+template <int KBOX, int STAGES, int MODE, int TPS = 1, int HSLOTS = 2>
 __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_constant__ ConvParams p) {
-    using L = PxSmem<KBOX, STAGES>;
+    using L = PxSmem<KBOX, STAGES, TPS, HSLOTS>;
+    constexpr int kPxHaloSlots = HSLOTS;
     static_assert(MODE == MODE_STORE || MODE == MODE_HEAD, "conv_px_kernel modes");
     constexpr int kRowBytes = KBOX * 2;
     constexpr int kAccStride = 256;
@@ -110,7 +115,10 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
         // flat walk over (tile, chunk).  With two halo slots the NEXT halo tile is requested after weight tile kIssueTap
         // of the current chunk: by then the MMA warp (at most STAGES weight tiles behind) is done with the slot's
         // previous occupant, so the request never blocks the weight stream.
-        constexpr int kIssueTap = STAGES - 1 < 8 ? STAGES - 1 : 8;
+        // With three halo slots the next halo tile is simply requested before the current chunk's weights (its slot was
+        // freed two chunks ago).
+        constexpr int kStagesPerChunk = 9 / TPS;
+        constexpr int kIssueStage = HSLOTS >= 3 ? -1 : (STAGES - 1 < kStagesPerChunk - 1 ? STAGES - 1 : kStagesPerChunk - 1);
         int s = 0, sh = 0;
         uint32_t ph = 0, phh = 0;
         auto load_halo = [&](int tile, int chunk) {
@@ -130,16 +138,19 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
         while (tile < num_tiles) {
             int ntile = tile, nchunk = chunk + 1;
             if (nchunk == p.chunks) { nchunk = 0; ntile += gridDim.x; }
+            if (kIssueStage < 0 && ntile < num_tiles) load_halo(ntile, nchunk);
             int kcol = chunk * KBOX;
-            for (int tap = 0; tap < 9; ++tap, kcol += p.tap_kstride) {
+            for (int st = 0; st < kStagesPerChunk; ++st, kcol += TPS * p.tap_kstride) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(&full_bar[s], L::kABox);
-                    tma_load_2d(stage_base + s * L::kStage, &p.tmap_b, &full_bar[s], kcol, 0);
+                    mbar_expect_tx(&full_bar[s], L::kStage);
+#pragma unroll
+                    for (int j = 0; j < TPS; ++j)
+                        tma_load_2d(stage_base + s * L::kStage + j * L::kABox, &p.tmap_b, &full_bar[s], kcol + j * p.tap_kstride, 0);
                 }
                 __syncwarp();
                 if (++s == STAGES) { s = 0; ph ^= 1; }
-                if (tap == kIssueTap && ntile < num_tiles) load_halo(ntile, nchunk);
+                if (st == kIssueStage && ntile < num_tiles) load_halo(ntile, nchunk);
             }
             tile = ntile;
             chunk = nchunk;
@@ -162,25 +173,55 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
             for (int chunk = 0; chunk < p.chunks; ++chunk) {
                 mbar_wait(&hfull_bar[sh], phh);
                 const uint32_t h_addr = h0 + sh * L::kHaloSlot;
-                for (int tap = 0; tap < 9; ++tap) {
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const int ky = tap / 3, kx = tap - 3 * ky;
-                    const uint32_t h_tap = h_addr + (ky * kPxHaloW + kx) * kRowBytes;
-                    if (elect_one()) {
-                        const uint64_t adesc = umma_smem_desc<kRowBytes>(w0 + s * L::kStage);                    // M side: weights
-                        const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((h_tap & 0x3FFFFu) >> 4);       // N side: pixels
+                if constexpr (TPS == 1) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const int ky = tap / 3, kx = tap - 3 * ky;
+                        const uint32_t h_tap = h_addr + (ky * kPxHaloW + kx) * kRowBytes;
+                        if (elect_one()) {
+                            const uint64_t adesc = umma_smem_desc<kRowBytes>(w0 + s * L::kStage);                    // M side: weights
+                            const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((h_tap & 0x3FFFFu) >> 4);       // N side: pixels
 #pragma unroll
-                        for (int k = 0; k < KBOX / 16; ++k)
-                            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (chunk | tap | k) != 0 ? 1u : 0u);
-                        umma_commit(&empty_bar[s]);
-                        if (tap == 8) {
-                            umma_commit(&hempty_bar[sh]);
-                            if (chunk == p.chunks - 1) umma_commit(&tfull_bar[acc]);
+                            for (int k = 0; k < KBOX / 16; ++k)
+                                umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (chunk | tap | k) != 0 ? 1u : 0u);
+                            umma_commit(&empty_bar[s]);
+                            if (tap == 8) {
+                                umma_commit(&hempty_bar[sh]);
+                                if (chunk == p.chunks - 1) umma_commit(&tfull_bar[acc]);
+                            }
                         }
+                        __syncwarp();
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
-                    __syncwarp();
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                } else {
+                    // one kernel row (three taps) per stage: one barrier round trip, then a straight-line block of
+                    // 3 * KBOX/16 MMAs with compile-time descriptor offsets
+                    const uint64_t bdesc_c = bdesc0 | static_cast<uint64_t>((h_addr & 0x3FFFFu) >> 4);
+#pragma unroll
+                    for (int t0 = 0; t0 < 9; t0 += TPS) {
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t adesc_s = umma_smem_desc<kRowBytes>(w0 + s * L::kStage);
+#pragma unroll
+                            for (int j = 0; j < TPS; ++j) {
+                                const int tap = t0 + j, ky = tap / 3, kx = tap - 3 * ky;
+                                const uint64_t adesc = adesc_s + static_cast<uint64_t>((j * L::kABox) >> 4);
+                                const uint64_t bdesc = bdesc_c + static_cast<uint64_t>(((ky * kPxHaloW + kx) * kRowBytes) >> 4);
+#pragma unroll
+                                for (int k = 0; k < KBOX / 16; ++k)
+                                    umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (tap | k) != 0 ? 1u : (chunk != 0 ? 1u : 0u));
+                            }
+                            umma_commit(&empty_bar[s]);
+                            if (t0 + TPS == 9) {
+                                umma_commit(&hempty_bar[sh]);
+                                if (chunk == p.chunks - 1) umma_commit(&tfull_bar[acc]);
+                            }
+                        }
+                        __syncwarp();
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
                 }
                 if (++sh == kPxHaloSlots) { sh = 0; phh ^= 1; }
             }

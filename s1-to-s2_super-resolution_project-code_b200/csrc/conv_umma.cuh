@@ -132,12 +132,13 @@ __device__ __forceinline__ void philox_normal4(const HeadParams& hp, uint32_t pi
     }
 }
 
-template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, int SBUF = 1>
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, int SBUF = 1, int TPS = 1>
 struct ConvSmem {
     static constexpr int kABox = 128 * KBOX * 2;
     static constexpr int kBBox = (BLOCK_N / CTAS) * KBOX * 2;   // this CTA's share of the weight rows
     static constexpr int kARing = HALO ? kHaloSlots * Halo<KBOX>::kSlot : 0;
-    static constexpr int kStage = HALO ? kBBox : BOXES * (kABox + kBBox);   // halo mode: the ring holds weight tiles only
+    static constexpr int kStage = HALO ? TPS * kBBox : BOXES * (kABox + kBBox);   // halo mode: the ring holds weight tiles only
+                                                                                  // (TPS taps of one channel chunk per stage)
     // output staging for the TMA store: one [rows][32 channels] fp16 sub-tile (64-byte rows, 64B swizzle) per
     // 32-column accumulator chunk; rows = 128 pixels, or the 32 pooled pixels of the tile
     static constexpr int kSubRows = MODE == MODE_POOL ? 32 : 128;
@@ -147,8 +148,9 @@ struct ConvSmem {
                                                               // TMA store's smem-read latency
     static constexpr int kBias = 1536 * 4;
     static constexpr int kBytes = 1024 /*align slack*/ + kARing + STAGES * kStage + kStaging + kBias + 256 /*barriers*/;
-    static_assert(kStage % 512 == 0, "stage alignment");
+    static_assert(kStage % 512 == 0 && kBBox % 512 == 0, "stage alignment");
     static_assert(!HALO || (BOXES == 1 && STAGES <= 10), "halo mode");
+    static_assert(TPS == 1 || (HALO && (TPS == 3 || TPS == 9)), "taps per stage");
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
@@ -178,13 +180,20 @@ __device__ __forceinline__ float range_scale(uint32_t amax_bits, float& s) {
 
 // CTAS = 2: CTA pair (cta_group::2, M = 256 per MMA, weight rows split across the pair).  CTAS = 1: single-CTA MMAs
 // (M = 128), kept for A/B measurements of the pairing itself.
-// WRES (halo mode, one chunk per tap, STAGES >= 9): the nine weight tiles are loaded once per CTA and stay resident;
-// the ring then only carries activation halo tiles (inc.0: K = 16 per tap would otherwise be TMA-latency bound).
-template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, bool WRES = false, int SBUF = 1>
-__global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(256, 1)
+// TPS (halo mode): weight tiles of TPS consecutive taps (one kernel row, or all nine) of a channel chunk share one ring
+// stage and one barrier round trip, and the MMA warp issues them from a fully unrolled block with compile-time
+// descriptor offsets.  The issue loop costs ~300 cycles per stage whatever it carries (ncu source view, r1s profiles), so
+// short-K stages (KBOX = 16 / 32: one / two 128-cycle MMAs per tap) were issue-bound at TPS = 1.
+// WRES (halo mode, one chunk per tap, TPS = 9, one stage): the nine weight tiles are loaded once per CTA and stay
+// resident; the ring then only carries activation halo tiles (inc.0).
+// EPIWG: epilogue warpgroups (warps 4..7 [, 8..11]); with two, each drains half of the accumulator's columns.
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, bool WRES = false, int SBUF = 1,
+          int TPS = 1, int EPIWG = 1>
+__global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(128 + 128 * EPIWG, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
-    static_assert(!WRES || (HALO && STAGES >= 9), "resident weights need halo mode and nine slots");
-    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE, CTAS, HALO, SBUF>;
+    static_assert(!WRES || (HALO && TPS == 9 && STAGES == 1), "resident weights: halo mode, all nine taps in one stage");
+    static_assert(EPIWG == 1 || (EPIWG == 2 && MODE != MODE_HEAD), "epilogue warpgroups");
+    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE, CTAS, HALO, SBUF, TPS>;
     constexpr bool kPair = CTAS == 2;
     constexpr bool kTmaStore = (MODE != MODE_HEAD);
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
@@ -232,7 +241,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);        // one multicast commit
-            mbar_init(&tempty_bar[a], 4 * CTAS); // one arrive per epilogue warp of every CTA of the group
+            mbar_init(&tempty_bar[a], 4 * CTAS * EPIWG); // one arrive per epilogue warp of every CTA of the group
         }
         if constexpr (HALO) {
             for (int a = 0; a < kHaloSlots; ++a) {
@@ -279,15 +288,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         };
         int tile = cluster_id, chunk = 0;
         if constexpr (WRES) {                     // one N tile, one chunk per tap: all weights of the layer, once
-            for (int tap = 0; tap < 9; ++tap) {
-                const uint32_t bar = kPair ? mapa_shared(smem_u32(&full_bar[tap]), 0) : smem_u32(&full_bar[tap]);
-                if (elect_one()) {
-                    if (rank == 0) mbar_expect_tx(&full_bar[tap], CTAS * L::kBBox);
-                    tma_load_2d_g<kPair>(stage_base + tap * L::kStage, &p.tmap_b, bar, tap * p.tap_kstride,
+            const uint32_t bar = kPair ? mapa_shared(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
+            if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(&full_bar[0], CTAS * 9 * L::kBBox);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap)
+                    tma_load_2d_g<kPair>(stage_base + tap * L::kBBox, &p.tmap_b, bar, tap * p.tap_kstride,
                                          static_cast<int>(rank) * (BLOCK_N / CTAS));
-                }
-                __syncwarp();
             }
+            __syncwarp();
         }
         if (tile < num_tiles) load_halo(tile, 0);
         while (tile < num_tiles) {
@@ -296,12 +305,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             if (ntile < num_tiles) load_halo(ntile, nchunk);
             const int b_row0 = (tile % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
             int kcol = chunk * KBOX;
-            for (int tap = 0; tap < (WRES ? 0 : 9); ++tap, kcol += p.tap_kstride) {
+            for (int tap = 0; tap < (WRES ? 0 : 9); tap += TPS, kcol += TPS * p.tap_kstride) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 const uint32_t bar = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
                 if (elect_one()) {
-                    if (rank == 0) mbar_expect_tx(&full_bar[s], CTAS * L::kBBox);
-                    tma_load_2d_g<kPair>(stage_base + s * L::kStage, &p.tmap_b, bar, kcol, b_row0);
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], CTAS * L::kStage);
+#pragma unroll
+                    for (int j = 0; j < TPS; ++j)
+                        tma_load_2d_g<kPair>(stage_base + s * L::kStage + j * L::kBBox, &p.tmap_b, bar,
+                                             kcol + j * p.tap_kstride, b_row0);
                 }
                 __syncwarp();
                 if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -316,6 +328,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             uint32_t ph = 0, pha = 0;
             int acc = 0;
             uint32_t acc_ph = 0;
+            [[maybe_unused]] bool wres_ready = false;
             const uint32_t b0 = smem_u32(stage_base), a0 = smem_u32(a_ring);
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
@@ -329,26 +342,60 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     adesc0 |= static_cast<uint64_t>((kHaloW * kRowBytes) >> 4) << 32;
                     adesc0 |= static_cast<uint64_t>(1) << 46;
                     adesc0 |= (kRowBytes == 128 ? 2ull : (kRowBytes == 64 ? 4ull : 6ull)) << 61;
-                    for (int tap = 0; tap < 9; ++tap) {
-                        if constexpr (WRES) { s = tap; ph = 0; }      // resident weights: phase 0 completed once, for good
-                        mbar_wait(&full_bar[s], ph);
-                        tc_fence_after();
-                        const int ky = tap / 3, kx = tap - 3 * ky;
-                        const uint32_t a_tap = a_addr + (ky * kHaloW + kx) * kRowBytes;
-                        if (elect_one()) {
-                            const uint64_t adesc = adesc0 | static_cast<uint64_t>((a_tap & 0x3FFFFu) >> 4);
-                            const uint64_t bdesc = umma_smem_desc<kRowBytes>(b0 + s * L::kStage);
+                    if constexpr (TPS == 1) {
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&full_bar[s], ph);
+                            tc_fence_after();
+                            const int ky = tap / 3, kx = tap - 3 * ky;
+                            const uint32_t a_tap = a_addr + (ky * kHaloW + kx) * kRowBytes;
+                            if (elect_one()) {
+                                const uint64_t adesc = adesc0 | static_cast<uint64_t>((a_tap & 0x3FFFFu) >> 4);
+                                const uint64_t bdesc = umma_smem_desc<kRowBytes>(b0 + s * L::kStage);
 #pragma unroll
-                            for (int k = 0; k < KBOX / 16; ++k)
-                                umma_f16_g<kPair>(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (chunk | tap | k) != 0 ? 1u : 0u);
-                            if constexpr (!WRES) umma_commit_g<kPair>(&empty_bar[s]);
-                            if (tap == 8) {
-                                umma_commit_g<kPair>(&aempty_bar[sa]);
-                                if (chunk == p.chunks - 1) umma_commit_g<kPair>(&tfull_bar[acc]);
+                                for (int k = 0; k < KBOX / 16; ++k)
+                                    umma_f16_g<kPair>(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (chunk | tap | k) != 0 ? 1u : 0u);
+                                umma_commit_g<kPair>(&empty_bar[s]);
+                                if (tap == 8) {
+                                    umma_commit_g<kPair>(&aempty_bar[sa]);
+                                    if (chunk == p.chunks - 1) umma_commit_g<kPair>(&tfull_bar[acc]);
+                                }
                             }
+                            __syncwarp();
+                            if (++s == STAGES) { s = 0; ph ^= 1; }
                         }
-                        __syncwarp();
-                        if constexpr (!WRES) { if (++s == STAGES) { s = 0; ph ^= 1; } }
+                    } else {
+                        // TPS taps per stage: one barrier round trip, then a straight-line block of TPS * KBOX/16 MMAs whose
+                        // descriptors differ from the stage's base descriptors by compile-time constants
+                        const uint64_t adesc_c = adesc0 | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
+#pragma unroll
+                        for (int t0 = 0; t0 < 9; t0 += TPS) {
+                            if constexpr (WRES) {
+                                if (!wres_ready) { mbar_wait(&full_bar[0], 0); wres_ready = true; }
+                            } else {
+                                mbar_wait(&full_bar[s], ph);
+                            }
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t bdesc_s = umma_smem_desc<kRowBytes>(b0 + (WRES ? 0 : s) * L::kStage);
+#pragma unroll
+                                for (int j = 0; j < TPS; ++j) {
+                                    const int tap = t0 + j, ky = tap / 3, kx = tap - 3 * ky;
+                                    const uint64_t adesc = adesc_c + static_cast<uint64_t>(((ky * kHaloW + kx) * kRowBytes) >> 4);
+                                    const uint64_t bdesc = bdesc_s + static_cast<uint64_t>((j * L::kBBox) >> 4);
+#pragma unroll
+                                    for (int k = 0; k < KBOX / 16; ++k)
+                                        umma_f16_g<kPair>(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc,
+                                                          (tap | k) != 0 ? 1u : (chunk != 0 ? 1u : 0u));
+                                }
+                                if constexpr (!WRES) umma_commit_g<kPair>(&empty_bar[s]);
+                                if (t0 + TPS == 9) {
+                                    umma_commit_g<kPair>(&aempty_bar[sa]);
+                                    if (chunk == p.chunks - 1) umma_commit_g<kPair>(&tfull_bar[acc]);
+                                }
+                            }
+                            __syncwarp();
+                            if constexpr (!WRES) { if (++s == STAGES) { s = 0; ph ^= 1; } }
+                        }
                     }
                     if (++sa == kHaloSlots) { sa = 0; pha ^= 1; }
                 }
@@ -443,7 +490,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             }
         }
     } else if (warp >= 4) {
-        // ================================================================= epilogue (4 warps, 1 pixel per thread)
+        // ================================================================= epilogue (1 pixel per thread; with two
+        // warpgroups, group g drains the column chunks [g * kChunksWg, ...) of the same accumulator)
+        constexpr int kChunks = BLOCK_N / 32;
+        constexpr int kChunksWg = (kChunks + EPIWG - 1) / EPIWG;
+        const int c_lo = EPIWG == 1 ? 0 : ((warp - 4) >> 2) * kChunksWg;
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const int tw = 1 << p.tw_log2;
@@ -568,13 +619,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 }
                 if constexpr (kTmaStore) {
                     if (warp == 4 && lane == 0) bulk_wait_read<SBUF - 1>();   // this buffer's previous stores have read it
-                    named_bar_sync(1, 128);
+                    named_bar_sync(1, 128 * EPIWG);
                 }
                 const bool first = (p.flags & LAYER_FLAG_FIRST) != 0;
                 const float s_bias = first ? 1.f : s_dn;      // first layer: unscaled inputs, scale the result
                 const float s_post = first ? s_dn : 1.f;
 #pragma unroll
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                for (int cc = 0; cc < kChunksWg; ++cc) {
+                    const int c = c_lo + cc;
+                    if (EPIWG > 1 && c >= kChunks) break;
                     uint32_t r[32];
                     tmem_ld32(taddr + c * 32, r);
                     tmem_ld_wait();
@@ -610,7 +663,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 if (lane == 0) mbar_arrive_cluster(tempty_leader);
                 if constexpr (kTmaStore) {
                     fence_proxy_async_smem();
-                    named_bar_sync(1, 128);
+                    named_bar_sync(1, 128 * EPIWG);
                     if (warp == 4 && lane == 0) {
                         const int on0 = tn << (7 - p.tw_log2 - p.th_log2);
                         if constexpr (MODE == MODE_CONVT) {

@@ -168,38 +168,41 @@ CUtensorMapSwizzle swizzle_for(int kbox) {
 }
 
 // ---------------------------------------------------------------------------------------------- layers
-enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_STORE256_1, K_POOL256_1, K_PX_STORE, K_PX_HEAD, K_PX_HEAD32, K_HSTORE, K_HPOOL, K_HSTORE256, K_HPOOL256, K_HINC, K_HC96IN, K_COUNT };
+enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_STORE256_1, K_POOL256_1, K_PX_STORE, K_PX_HEAD, K_PX_HEAD32, K_HSTORE, K_HPOOL, K_HSTORE256, K_HPOOL256, K_HINC, K_HC96IN, K_HINC_1WG, K_PX_HEAD32_T1, K_CONVT_2, K_CONVT256_2, K_COUNT };
 
 struct KernelInfo {
     void (*fn)(const ConvParams);
-    int block_n, kbox, boxes, smem, mode, ctas;
+    int block_n, kbox, boxes, smem, mode, ctas, threads;
     bool px;                 // conv_px_kernel (pixels on N) instead of conv_umma_kernel
     bool halo;               // conv_umma_kernel halo mode (8 x 16 tile, one activation halo tile per chunk)
 };
 
-template <int BN, int KB, int BX, int ST, int MODE, int CTAS = 2, bool HALO = false, bool WRES = false, int SBUF = 1>
+template <int BN, int KB, int BX, int ST, int MODE, int CTAS = 2, bool HALO = false, bool WRES = false, int SBUF = 1,
+          int TPS = 1, int EPIWG = 1>
 KernelInfo make_kernel() {
     KernelInfo k;
-    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS, HALO, WRES, SBUF>;
+    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS, HALO, WRES, SBUF, TPS, EPIWG>;
+    k.threads = 128 + 128 * EPIWG;
     k.ctas = CTAS;
     k.px = false;
     k.halo = HALO;
     k.block_n = BN;
     k.kbox = KB;
     k.boxes = BX;
-    k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS, HALO, SBUF>::kBytes;
+    k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS, HALO, SBUF, TPS>::kBytes;
     k.mode = MODE;
     return k;
 }
 
-template <int KB, int ST, int MODE>
+template <int KB, int ST, int MODE, int TPS = 1, int HSLOTS = 2>
 KernelInfo make_px_kernel() {
     KernelInfo k;
-    k.fn = conv_px_kernel<KB, ST, MODE>;
+    k.fn = conv_px_kernel<KB, ST, MODE, TPS, HSLOTS>;
+    k.threads = kPxThreads;
     k.block_n = 96;
     k.kbox = KB;
     k.boxes = 1;
-    k.smem = PxSmem<KB, ST>::kBytes;
+    k.smem = PxSmem<KB, ST, TPS, HSLOTS>::kBytes;
     k.mode = MODE;
     k.ctas = 1;
     k.px = true;
@@ -226,11 +229,20 @@ const KernelInfo* kernel_table() {
         t[K_HPOOL] = make_kernel<192, 64, 1, 10, MODE_POOL, 2, true>();
         t[K_HSTORE256] = make_kernel<256, 64, 1, 5, MODE_STORE, 2, true>();
         t[K_HPOOL256] = make_kernel<256, 64, 1, 8, MODE_POOL, 2, true>();
-        t[K_HINC] = make_kernel<96, 16, 1, 9, MODE_STORE, 2, true, true, 4>();  // inc.0: 32-byte rows, resident weights, 4 staging buffers
-        t[K_HC96IN] = make_kernel<192, 32, 1, 10, MODE_STORE, 2, true>();   // down1.0.0: Cin = 96 as three 32-channel chunks
+        // Short-K layers: several taps per ring stage (the MMA issue loop costs ~300 cycles per stage: profiles/r1s source view)
+        t[K_HINC] = make_kernel<96, 16, 1, 1, MODE_STORE, 2, true, true, 4, 9, 2>();   // inc.0: 32-byte rows, nine resident weight tiles,
+                                                                                       // 4 staging buffers, two epilogue warpgroups
+        t[K_HINC_1WG] = make_kernel<96, 16, 1, 1, MODE_STORE, 2, true, true, 4, 9, 1>();   // A/B: one epilogue warpgroup
+        t[K_HC96IN] = make_kernel<192, 32, 1, 6, MODE_STORE, 2, true, false, 1, 3>();  // down1.0.0: exact K = 96 per tap as three
+                                                                                       // 32-channel chunks, one kernel row per stage
         t[K_PX_STORE] = make_px_kernel<64, 5, MODE_STORE>();            // conv1.0: pixels on N (see conv_px.cuh)
         t[K_PX_HEAD] = make_px_kernel<64, 5, MODE_HEAD>();              // conv1.2 + outc + scheduler, K padded 96 -> 128 per tap
-        t[K_PX_HEAD32] = make_px_kernel<32, 10, MODE_HEAD>();            // same with exact 32-channel chunks (default)
+        t[K_PX_HEAD32] = make_px_kernel<32, 4, MODE_HEAD, 3, 3>();        // same with exact 32-channel chunks, one kernel row per
+                                                                          // stage, three halo slots (default)
+        t[K_PX_HEAD32_T1] = make_px_kernel<32, 10, MODE_HEAD>();          // A/B: one tap per stage (S1S2_OLD_ISSUE=1)
+        t[K_CONVT_2] = make_kernel<192, 64, 1, 4, MODE_CONVT, 2, false, false, 2, 1, 2>();   // two staging buffers + two epilogue
+        t[K_CONVT256_2] = make_kernel<256, 64, 1, 4, MODE_CONVT, 2, false, false, 1, 1, 2>(); // warpgroups: the transposed convs are
+                                                                                              // epilogue-bound (K = Cin only)
         t[K_STORE256_1] = make_kernel<256, 64, 1, 3, MODE_STORE, 1>();   // single-CTA variants: A/B measurement only
         t[K_POOL256_1] = make_kernel<256, 64, 1, 4, MODE_POOL, 1>();     // (S1S2_SINGLE_CTA_256=1)
         t[K_HEAD] = make_kernel<96, 32, 3, 6, MODE_HEAD>();     // conv1.2 + outc + scheduler
@@ -245,6 +257,7 @@ struct Layer {
     int level;               // input resolution = (H >> level, W >> level)
     int cin;                 // K per tap (padded for inc and down1.0.0)
     int cin_real = 0;        // input channels of the state_dict tensor when cin is padded (0: same as cin)
+    bool first = false;      // inc.0: reads the 16-slot pixel record, applies the range scale
     int ntot;                // GEMM N (CONVT: 4 * cout)
     int cout;                // real output channels per pixel
     int taps_w;
@@ -470,7 +483,7 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
     p.chunks = L.cin / k.kbox;
     p.tap_kstride = L.cin;
     p.cout = L.cout;
-    p.flags = (L.kid == K_INC || L.kid == K_HINC) ? LAYER_FLAG_FIRST : 0;
+    p.flags = L.first ? LAYER_FLAG_FIRST : 0;
     return S1S2_OK;
 }
 
@@ -492,7 +505,7 @@ int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, cudaS
     p.amax_in = amax_in;
     const int group_tiles = ((p.num_m_tiles + k.ctas - 1) / k.ctas) * p.num_n_tiles;   // one CTA group per (ctas M tiles, 1 N tile)
     const int clusters = group_tiles < h->num_sms / k.ctas ? group_tiles : h->num_sms / k.ctas;
-    k.fn<<<k.ctas * clusters, 256, k.smem, st>>>(p);                       // __cluster_dims__(ctas, 1, 1)
+    k.fn<<<k.ctas * clusters, k.threads, k.smem, st>>>(p);                 // __cluster_dims__(ctas, 1, 1)
     CK(cudaGetLastError());
     ++h->launches;
     return S1S2_OK;
@@ -635,10 +648,11 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     // cat1 = [up1 (96) | inc (96) | 32 channels that stay zero]: down1.0.0 reads [inc | zeros] as Cin = 128 = two
     // 64-channel chunks (zero weights on the padding) and so runs in halo mode like every other 3x3 layer.
     add("inc.0",       K_INC,    0,  16,  96,   96,  3,   h->xin16,    16,   cat1 + 96,    224);
-    if (getenv("S1S2_NO_PAD96") == nullptr) {
+    h->layers.back().first = true;
+    if (getenv("S1S2_PAD96") != nullptr) {    // A/B: K padded to 128 per tap (two 64-channel chunks, a quarter of the MMAs wasted)
         add("down1.0.0", K_STORE,  0,  128, 192,  192, 3,   cat1 + 96,   224,  d1a,          192);
         h->layers.back().cin_real = 96;
-    } else {                                   // A/B: exact K = 96 per tap as three 32-channel chunks, no halo
+    } else {                                   // exact K = 96 per tap as three 32-channel chunks
         add("down1.0.0", K_C96IN,  0,  96,  192,  192, 3,   cat1 + 96,   224,  d1a,          192);
     }
     add("down1.0.2",   K_POOL,   0,  192, 192,  192, 3,   d1a,         192,  cat2 + 192,   384);
@@ -660,7 +674,7 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
         for (Layer& L : h->layers) {
             if (L.taps_w != 3) continue;
             if (L.kid == K_INC) L.kid = K_HINC;
-            else if (L.kid == K_C96IN && getenv("S1S2_HALO_C96") != nullptr) L.kid = K_HC96IN;   // measured slower (small stages)
+            else if (L.kid == K_C96IN) L.kid = K_HC96IN;
             if (L.cin % 64 != 0) continue;
             if (L.kid == K_STORE) L.kid = K_HSTORE;
             else if (L.kid == K_POOL) L.kid = K_HPOOL;
@@ -672,6 +686,19 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
         for (Layer& L : h->layers) {
             if (L.kid == K_N96) L.kid = K_PX_STORE;
             if (L.kid == K_HEAD) L.kid = getenv("S1S2_PX_HEAD64") != nullptr ? K_PX_HEAD : K_PX_HEAD32;
+        }
+    }
+    if (getenv("S1S2_OLD_ISSUE") != nullptr) {   // A/B: one tap per stage in the head, one epilogue warpgroup in inc.0
+        for (Layer& L : h->layers) {
+            if (L.kid == K_PX_HEAD32) L.kid = K_PX_HEAD32_T1;
+            if (L.kid == K_HINC) L.kid = K_HINC_1WG;
+        }
+    }
+    if (getenv("S1S2_CONVT_2WG") != nullptr) {   // A/B: two epilogue warpgroups in the transposed convs (measured neutral:
+                                                 // up1 0.312 vs 0.325 ms at batch 64 -- they are not epilogue-compute bound)
+        for (Layer& L : h->layers) {
+            if (L.kid == K_CONVT) L.kid = K_CONVT_2;
+            if (L.kid == K_CONVT256) L.kid = K_CONVT256_2;
         }
     }
     if (getenv("S1S2_SINGLE_CTA_256") != nullptr) {
@@ -743,7 +770,7 @@ int s1s2_load_weights(s1s2_handle* h, int n, const char* const* names, const flo
         const float *w = nullptr, *b = nullptr;
         const std::string nm = L.name;
         int rc;
-        if ((L.kid == K_INC || L.kid == K_HINC)) {
+        if (L.first) {
             if ((rc = find(nm + ".weight", 96 * 9 * 9, &w)) || (rc = find(nm + ".bias", 96, &b))) return rc;
             repack_inc_kernel<<<64, 256, 0, st>>>(w, L.w, 96);
             tile_bias_kernel<<<4, 256, 0, st>>>(b, L.bias, 96, 1);
