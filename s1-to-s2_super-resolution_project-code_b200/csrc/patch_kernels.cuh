@@ -17,82 +17,105 @@ namespace s1s2 {
 constexpr int kExtractThreads = 1024;
 constexpr int kStitchMaxC = 8;
 
+// All four kernels are templated on G, the number of consecutive pixels of an image row one thread handles per step:
+// G = 4 moves float4 / uchar4 (used when the row pitch, the window size, every window origin and the base pointers
+// are multiples of 4 elements -- Patch.py's 256 / stride 32 geometry), G = 1 is the general scalar path.  Same
+// arithmetic either way; only the association of the fp64 partial sums differs.
+template <int G>
+__device__ __forceinline__ void ld_f(const float* p, float (&o)[G]) {
+    if constexpr (G == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else {
+        o[0] = __ldg(p);
+    }
+}
+template <int G>
+__device__ __forceinline__ void st_f(float* p, const float (&v)[G]) {
+    if constexpr (G == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else p[0] = v[0];
+}
+template <int G>
+__device__ __forceinline__ void ld_b(const uint8_t* p, uint8_t (&o)[G]) {
+    if constexpr (G == 4) {
+        const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(p));
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else {
+        o[0] = __ldg(p);
+    }
+}
+template <int G>
+__device__ __forceinline__ void st_b(uint8_t* p, const uint8_t (&v)[G]) {
+    if constexpr (G == 4) *reinterpret_cast<uchar4*>(p) = make_uchar4(v[0], v[1], v[2], v[3]);
+    else p[0] = v[0];
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-// Sums three doubles over the block; every thread receives the totals.
-__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* scratch /* [3*32] */) {
+// Sums NV doubles over the block (up to 32 warps); every thread receives the totals.  red: [32][NV].
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double (*red)[NV]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    a = warp_sum(a);
-    b = warp_sum(b);
-    c = warp_sum(c);
-    __syncthreads();                 // scratch may still be read from a previous call
-    if (lane == 0) {
-        scratch[warp] = a;
-        scratch[32 + warp] = b;
-        scratch[64 + warp] = c;
+    __syncthreads();                 // red may still be read from a previous call
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double s = warp_sum(v[i]);
+        if (lane == 0) red[warp][i] = s;
     }
     __syncthreads();
-    a = lane < nw ? scratch[lane] : 0.0;
-    b = lane < nw ? scratch[32 + lane] : 0.0;
-    c = lane < nw ? scratch[64 + lane] : 0.0;
-    a = warp_sum(a);
-    b = warp_sum(b);
-    c = warp_sum(c);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(lane < nw ? red[lane][i] : 0.0);
 }
 
 // One CTA per window.  scene f32[4,SH,SW]; vmask u8[SH,SW] or nullptr; origins i32[N,2] (row, col);
 // cond f32[N,4,ps,ps]; mask u8[N,ps,ps]; valid_ratio f32[N] or nullptr.
-// Statistics are accumulated in fp64 (numpy uses fp32 pairwise sums; the two agree to ~1 ulp of the mean).
-__global__ void __launch_bounds__(kExtractThreads) tile_extract_kernel(const float* __restrict__ scene,
-                                                                       const uint8_t* __restrict__ vmask, int SH, int SW,
-                                                                       const int32_t* __restrict__ origins, int ps,
-                                                                       float* __restrict__ cond, uint8_t* __restrict__ mask,
-                                                                       float* __restrict__ valid_ratio) {
-    __shared__ double scratch[96];
+// Two coalesced passes over the window (the second one is served by L2): masked sum / sum of squares of HH and HV in
+// fp64 (numpy uses fp32 pairwise sums; the two agree to ~1 ulp of the mean), then normalise + write.
+template <int G>
+__device__ __forceinline__ void tile_extract_body(const float* __restrict__ scene, const uint8_t* __restrict__ vmask, int SH,
+                                                  int SW, int r0, int c0, int ps, float* __restrict__ cond,
+                                                  uint8_t* __restrict__ mask, float* __restrict__ valid_ratio,
+                                                  double (*red)[5]) {
     const int p = blockIdx.x;
-    const int r0 = origins[2 * p], c0 = origins[2 * p + 1];
     const size_t plane = static_cast<size_t>(SH) * SW;
     const int npix = ps * ps;
+    const int gpr = ps / G, ngroups = ps * gpr;          // groups per window row, per window
 
-    auto valid_at = [&](size_t g, float v0, float v1, float v2, float v3) {
-        bool ok = isfinite(v0) && isfinite(v1) && isfinite(v2) && isfinite(v3);
-        if (vmask != nullptr) ok = ok && vmask[g] != 0;
-        return ok;
-    };
-
-    double s0 = 0.0, s1 = 0.0, cnt = 0.0;
-    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
-        const int y = i / ps, x = i - y * ps;
+    double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};             // sum HH, sum HH^2, sum HV, sum HV^2, count
+    for (int i = threadIdx.x; i < ngroups; i += blockDim.x) {
+        const int y = i / gpr, x = (i - y * gpr) * G;
         const size_t g = static_cast<size_t>(r0 + y) * SW + (c0 + x);
-        const float v0 = scene[g], v1 = scene[plane + g], v2 = scene[2 * plane + g], v3 = scene[3 * plane + g];
-        if (valid_at(g, v0, v1, v2, v3)) {
-            s0 += v0;
-            s1 += v1;
-            cnt += 1.0;
+        float v0[G], v1[G], v2[G], v3[G];
+        uint8_t vm[G];
+        ld_f<G>(scene + g, v0);
+        ld_f<G>(scene + plane + g, v1);
+        ld_f<G>(scene + 2 * plane + g, v2);
+        ld_f<G>(scene + 3 * plane + g, v3);
+        if (vmask != nullptr) ld_b<G>(vmask + g, vm);
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            bool ok = isfinite(v0[k]) && isfinite(v1[k]) && isfinite(v2[k]) && isfinite(v3[k]);
+            if (vmask != nullptr) ok = ok && vm[k] != 0;
+            if (ok) {
+                const double d0 = v0[k], d1 = v1[k];
+                a[0] += d0;
+                a[1] = fma(d0, d0, a[1]);
+                a[2] += d1;
+                a[3] = fma(d1, d1, a[3]);
+                a[4] += 1.0;
+            }
         }
     }
-    block_sum3(s0, s1, cnt, scratch);
-    const double m0 = cnt > 0.0 ? s0 / cnt : 0.0, m1 = cnt > 0.0 ? s1 / cnt : 0.0;
-
-    double q0 = 0.0, q1 = 0.0, dummy = 0.0;
-    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
-        const int y = i / ps, x = i - y * ps;
-        const size_t g = static_cast<size_t>(r0 + y) * SW + (c0 + x);
-        const float v0 = scene[g], v1 = scene[plane + g], v2 = scene[2 * plane + g], v3 = scene[3 * plane + g];
-        if (valid_at(g, v0, v1, v2, v3)) {
-            const double d0 = v0 - m0, d1 = v1 - m1;
-            q0 += d0 * d0;
-            q1 += d1 * d1;
-        }
-    }
-    block_sum3(q0, q1, dummy, scratch);
+    block_sum<5>(a, red);
+    const double cnt = a[4];
+    const double m0 = cnt > 0.0 ? a[0] / cnt : 0.0, m1 = cnt > 0.0 ? a[2] / cnt : 0.0;
     float mu0 = static_cast<float>(m0), mu1 = static_cast<float>(m1);
-    float sd0 = cnt > 0.0 ? static_cast<float>(sqrt(q0 / cnt)) : 1.f;
-    float sd1 = cnt > 0.0 ? static_cast<float>(sqrt(q1 / cnt)) : 1.f;
+    float sd0 = cnt > 0.0 ? static_cast<float>(sqrt(fmax(a[1] / cnt - m0 * m0, 0.0))) : 1.f;
+    float sd1 = cnt > 0.0 ? static_cast<float>(sqrt(fmax(a[3] / cnt - m1 * m1, 0.0))) : 1.f;
     if (!isfinite(mu0)) mu0 = 0.f;
     if (!isfinite(mu1)) mu1 = 0.f;
     if (!isfinite(sd0) || static_cast<double>(sd0) < 1e-6) sd0 = 1.f;
@@ -100,113 +123,162 @@ __global__ void __launch_bounds__(kExtractThreads) tile_extract_kernel(const flo
 
     float* cp = cond + static_cast<size_t>(p) * 4 * npix;
     uint8_t* mp = mask + static_cast<size_t>(p) * npix;
-    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
-        const int y = i / ps, x = i - y * ps;
+    for (int i = threadIdx.x; i < ngroups; i += blockDim.x) {
+        const int y = i / gpr, x = (i - y * gpr) * G;
         const size_t g = static_cast<size_t>(r0 + y) * SW + (c0 + x);
-        const float v0 = scene[g], v1 = scene[plane + g], v2 = scene[2 * plane + g], v3 = scene[3 * plane + g];
-        const bool ok = valid_at(g, v0, v1, v2, v3);
-        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-        if (ok) {
-            o0 = __fdiv_rn(__fsub_rn(v0, mu0), sd0);
-            o1 = __fdiv_rn(__fsub_rn(v1, mu1), sd1);
-            o2 = __fdiv_rn(v2, 90.f);
-            o3 = __fdiv_rn(v3, 1000.f);
-            if (!isfinite(o0)) o0 = 0.f;
-            if (!isfinite(o1)) o1 = 0.f;
+        float v0[G], v1[G], v2[G], v3[G];
+        uint8_t vm[G], mo[G];
+        ld_f<G>(scene + g, v0);
+        ld_f<G>(scene + plane + g, v1);
+        ld_f<G>(scene + 2 * plane + g, v2);
+        ld_f<G>(scene + 3 * plane + g, v3);
+        if (vmask != nullptr) ld_b<G>(vmask + g, vm);
+        float o0[G], o1[G], o2[G], o3[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            bool ok = isfinite(v0[k]) && isfinite(v1[k]) && isfinite(v2[k]) && isfinite(v3[k]);
+            if (vmask != nullptr) ok = ok && vm[k] != 0;
+            o0[k] = o1[k] = o2[k] = o3[k] = 0.f;
+            if (ok) {
+                o0[k] = __fdiv_rn(__fsub_rn(v0[k], mu0), sd0);
+                o1[k] = __fdiv_rn(__fsub_rn(v1[k], mu1), sd1);
+                o2[k] = __fdiv_rn(v2[k], 90.f);
+                o3[k] = __fdiv_rn(v3[k], 1000.f);
+                if (!isfinite(o0[k])) o0[k] = 0.f;
+                if (!isfinite(o1[k])) o1[k] = 0.f;
+            }
+            mo[k] = ok ? 1 : 0;
         }
-        cp[i] = o0;
-        cp[npix + i] = o1;
-        cp[2 * npix + i] = o2;
-        cp[3 * npix + i] = o3;
-        mp[i] = ok ? 1 : 0;
+        const int o = y * ps + x;
+        st_f<G>(cp + o, o0);
+        st_f<G>(cp + npix + o, o1);
+        st_f<G>(cp + 2 * npix + o, o2);
+        st_f<G>(cp + 3 * npix + o, o3);
+        st_b<G>(mp + o, mo);
     }
     if (valid_ratio != nullptr && threadIdx.x == 0) valid_ratio[p] = static_cast<float>(cnt / static_cast<double>(npix));
+}
+// allow_vec: the host found SW, ps and the base pointers 4-element aligned; the window's column origin decides per CTA.
+__global__ void __launch_bounds__(kExtractThreads) tile_extract_kernel(const float* __restrict__ scene,
+                                                                       const uint8_t* __restrict__ vmask, int SH, int SW,
+                                                                       const int32_t* __restrict__ origins, int ps,
+                                                                       float* __restrict__ cond, uint8_t* __restrict__ mask,
+                                                                       float* __restrict__ valid_ratio, int allow_vec) {
+    __shared__ double red[32][5];
+    const int r0 = origins[2 * blockIdx.x], c0 = origins[2 * blockIdx.x + 1];
+    if (allow_vec && (c0 & 3) == 0) tile_extract_body<4>(scene, vmask, SH, SW, r0, c0, ps, cond, mask, valid_ratio, red);
+    else tile_extract_body<1>(scene, vmask, SH, SW, r0, c0, ps, cond, mask, valid_ratio, red);
 }
 
 // ---------------------------------------------------------------------------------------------- quality filters
 // Patch.py's four window tests on the target (Patch.py:205-224): valid ratio, all-band variance, dark fraction
 // (:88-98) and Laplacian variance of band 3 with a symmetric window boundary (:100-114; scipy's convolve2d also
-// multiplies the 3x3 corners by zero, so a non-finite corner voids the sample).  One CTA per window, two passes.
+// multiplies the 3x3 corners by zero, so a non-finite corner voids the sample).  One CTA per window, ONE pass: every
+// statistic is a ratio of fp64 sums (count, sum y, sum y^2 per band, dark count, Laplacian moments).
 // stats[p][0..7] = valid_ratio, var[0..3], dark_fraction, laplacian_var, decision code (0 keep, 1 valid ratio, 2 flat,
 // 3 dark, 4 no texture).  Validity = build_mask (:41-49): every input and target band finite and colloc > 0.
 struct FilterThresholds {
     float valid_ratio, variance, dark_thr, dark_max_ratio, texture;
 };
 constexpr int kFilterThreads = 256;
+constexpr int kFilterMaxCi = 8;
 
-__device__ __forceinline__ void block_sum_n(double* v, int n, double (*red)[12]) {   // n <= 12; result in v on all threads
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    __syncthreads();
-    for (int i = 0; i < n; ++i) {
-        const double s = warp_sum(v[i]);
-        if (lane == 0) red[warp][i] = s;
-    }
-    __syncthreads();
-    for (int i = 0; i < n; ++i) v[i] = warp_sum(lane < nw ? red[lane][i] : 0.0);
-}
-
-__global__ void __launch_bounds__(kFilterThreads) tile_filter_kernel(const float* __restrict__ scene, int Ci,
-                                                                     const float* __restrict__ target,
-                                                                     const uint8_t* __restrict__ colloc, int SH, int SW,
-                                                                     const int32_t* __restrict__ origins, int ps,
-                                                                     FilterThresholds th, float* __restrict__ stats) {
-    __shared__ double red[kFilterThreads / 32][12];
+constexpr int kFilterVals = 13;   // count, sum y[4], sum y^2[4], dark, sum L, sum L^2, count L
+template <int G>
+__device__ __forceinline__ void tile_filter_body(const float* __restrict__ scene, int Ci, const float* __restrict__ target,
+                                                 const uint8_t* __restrict__ colloc, int SH, int SW, int r0, int c0, int ps,
+                                                 const FilterThresholds& th, float* __restrict__ stats,
+                                                 double (*red)[kFilterVals]) {
+    constexpr int NV = kFilterVals;
     const int p = blockIdx.x;
-    const int r0 = origins[2 * p], c0 = origins[2 * p + 1];
     const size_t plane = static_cast<size_t>(SH) * SW;
     const int npix = ps * ps;
-    auto valid_at = [&](size_t g) {
-        bool ok = colloc == nullptr || colloc[g] != 0;
-        for (int c = 0; c < Ci && ok; ++c) ok = isfinite(scene[c * plane + g]);
-        for (int c = 0; c < 4 && ok; ++c) ok = isfinite(target[c * plane + g]);
-        return ok;
-    };
-    // pass A: count, band sums, dark pixels
-    double a[12];
-    for (int i = 0; i < 12; ++i) a[i] = 0.0;
-    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
-        const int y = i / ps, x = i - y * ps;
-        const size_t g = static_cast<size_t>(r0 + y) * SW + (c0 + x);
-        if (!valid_at(g)) continue;
-        const float y0 = target[g], y1 = target[plane + g], y2 = target[2 * plane + g], y3 = target[3 * plane + g];
-        a[0] += 1.0;
-        a[1] += y0; a[2] += y1; a[3] += y2; a[4] += y3;
-        const float vis = __fdiv_rn(__fadd_rn(__fadd_rn(y0, y1), y2), 3.0f);
-        if (vis < th.dark_thr && y3 < th.dark_thr) a[5] += 1.0;
-    }
-    block_sum_n(a, 6, red);
-    const double cnt = a[0];
-    const double m0 = a[1] / cnt, m1 = a[2] / cnt, m2 = a[3] / cnt, m3 = a[4] / cnt;
-    const double dark = cnt > 0.0 ? a[5] / cnt : 1.0;
-    // pass B: squared deviations, Laplacian moments
-    double b[12];
-    for (int i = 0; i < 12; ++i) b[i] = 0.0;
+    const int gpr = ps / G, ngroups = ps * gpr;
     const float* b8 = target + 3 * plane;
-    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
-        const int y = i / ps, x = i - y * ps;
+    double a[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) a[i] = 0.0;
+    for (int i = threadIdx.x; i < ngroups; i += blockDim.x) {
+        const int y = i / gpr, x = (i - y * gpr) * G;
         const size_t g = static_cast<size_t>(r0 + y) * SW + (c0 + x);
-        if (!valid_at(g)) continue;
-        const double d0 = target[g] - m0, d1 = target[plane + g] - m1, d2 = target[2 * plane + g] - m2, d3 = target[3 * plane + g] - m3;
-        b[0] += d0 * d0; b[1] += d1 * d1; b[2] += d2 * d2; b[3] += d3 * d3;
-        // symmetric boundary: index -1 -> 0, ps -> ps-1
+        bool ok[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) ok[k] = true;
+        if (colloc != nullptr) {
+            uint8_t cl[G];
+            ld_b<G>(colloc + g, cl);
+#pragma unroll
+            for (int k = 0; k < G; ++k) ok[k] = cl[k] != 0;
+        }
+        for (int c = 0; c < Ci; ++c) {
+            float v[G];
+            ld_f<G>(scene + c * plane + g, v);
+#pragma unroll
+            for (int k = 0; k < G; ++k) ok[k] = ok[k] && isfinite(v[k]);
+        }
+        float yv[4][G];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            ld_f<G>(target + c * plane + g, yv[c]);
+#pragma unroll
+            for (int k = 0; k < G; ++k) ok[k] = ok[k] && isfinite(yv[c][k]);
+        }
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < G; ++k) any = any || ok[k];
+        if (!any) continue;
+        // band-3 rows above / below and the columns left / right of the group, symmetric boundary (-1 -> 0, ps -> ps-1)
         const int ym = y > 0 ? y - 1 : 0, yp = y < ps - 1 ? y + 1 : ps - 1;
-        const int xm = x > 0 ? x - 1 : 0, xp = x < ps - 1 ? x + 1 : ps - 1;
-        auto at = [&](int yy, int xx) { return b8[static_cast<size_t>(r0 + yy) * SW + (c0 + xx)]; };
-        const float c = at(y, x), n = at(ym, x), s = at(yp, x), w = at(y, xm), e = at(y, xp);
-        const float k0 = at(ym, xm), k1 = at(ym, xp), k2 = at(yp, xm), k3 = at(yp, xp);
-        if (isfinite(c) && isfinite(n) && isfinite(s) && isfinite(w) && isfinite(e) && isfinite(k0) && isfinite(k1) &&
-            isfinite(k2) && isfinite(k3)) {
-            const double L = static_cast<double>(n) + s + w + e - 4.0 * c;
-            b[4] += L; b[5] += L * L; b[6] += 1.0;
+        const int xm = x > 0 ? x - 1 : 0, xp = x + G < ps ? x + G : ps - 1;
+        float rm[G + 2], rc[G + 2], rp[G + 2];
+        {
+            const float* rowm = b8 + static_cast<size_t>(r0 + ym) * SW + c0;
+            const float* rowc = b8 + static_cast<size_t>(r0 + y) * SW + c0;
+            const float* rowp = b8 + static_cast<size_t>(r0 + yp) * SW + c0;
+            float t[G];
+            ld_f<G>(rowm + x, t);
+#pragma unroll
+            for (int k = 0; k < G; ++k) rm[k + 1] = t[k];
+            ld_f<G>(rowp + x, t);
+#pragma unroll
+            for (int k = 0; k < G; ++k) rp[k + 1] = t[k];
+#pragma unroll
+            for (int k = 0; k < G; ++k) rc[k + 1] = yv[3][k];
+            rm[0] = __ldg(rowm + xm); rm[G + 1] = __ldg(rowm + xp);
+            rc[0] = __ldg(rowc + xm); rc[G + 1] = __ldg(rowc + xp);
+            rp[0] = __ldg(rowp + xm); rp[G + 1] = __ldg(rowp + xp);
+        }
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            if (!ok[k]) continue;
+            const float y0 = yv[0][k], y1 = yv[1][k], y2 = yv[2][k], y3 = yv[3][k];
+            a[0] += 1.0;
+            const double d0 = y0, d1 = y1, d2 = y2, d3 = y3;
+            a[1] += d0; a[2] += d1; a[3] += d2; a[4] += d3;
+            a[5] = fma(d0, d0, a[5]); a[6] = fma(d1, d1, a[6]); a[7] = fma(d2, d2, a[7]); a[8] = fma(d3, d3, a[8]);
+            const float vis = __fdiv_rn(__fadd_rn(__fadd_rn(y0, y1), y2), 3.0f);
+            if (vis < th.dark_thr && y3 < th.dark_thr) a[9] += 1.0;
+            const float c = rc[k + 1], n = rm[k + 1], s = rp[k + 1], w = rc[k], e = rc[k + 2];
+            if (isfinite(c) && isfinite(n) && isfinite(s) && isfinite(w) && isfinite(e) && isfinite(rm[k]) && isfinite(rm[k + 2]) &&
+                isfinite(rp[k]) && isfinite(rp[k + 2])) {
+                // float32 like scipy's convolve2d on the reference's float32 arrays (Patch.py:104,112)
+                const double L = static_cast<double>(__fsub_rn(__fadd_rn(__fadd_rn(n, s), __fadd_rn(w, e)), __fmul_rn(4.f, c)));
+                a[10] += L; a[11] = fma(L, L, a[11]); a[12] += 1.0;
+            }
         }
     }
-    block_sum_n(b, 7, red);
+    block_sum<NV>(a, red);
     if (threadIdx.x == 0) {
+        const double cnt = a[0];
+        const double dark = cnt > 0.0 ? a[9] / cnt : 1.0;
         const float nanv = __int_as_float(0x7fc00000);
         float v[4];
-        for (int c = 0; c < 4; ++c) v[c] = cnt > 0.0 ? static_cast<float>(b[c] / cnt) : nanv;
+        for (int c = 0; c < 4; ++c) {
+            const double m = a[1 + c] / cnt;
+            v[c] = cnt > 0.0 ? static_cast<float>(fmax(a[5 + c] / cnt - m * m, 0.0)) : nanv;
+        }
         float lv = 0.f;
-        if (cnt > 0.0) lv = b[6] > 0.0 ? static_cast<float>(fmax(b[5] / b[6] - (b[4] / b[6]) * (b[4] / b[6]), 0.0)) : nanv;
+        if (cnt > 0.0) lv = a[12] > 0.0 ? static_cast<float>(fmax(a[11] / a[12] - (a[10] / a[12]) * (a[10] / a[12]), 0.0)) : nanv;
         const float vr = static_cast<float>(cnt / npix);
         int code = 0;
         if (vr < th.valid_ratio) code = 1;
@@ -218,21 +290,35 @@ __global__ void __launch_bounds__(kFilterThreads) tile_filter_kernel(const float
         o[5] = static_cast<float>(dark); o[6] = lv; o[7] = static_cast<float>(code);
     }
 }
+__global__ void __launch_bounds__(kFilterThreads, 4) tile_filter_kernel(const float* __restrict__ scene, int Ci,
+                                                                     const float* __restrict__ target,
+                                                                     const uint8_t* __restrict__ colloc, int SH, int SW,
+                                                                     const int32_t* __restrict__ origins, int ps,
+                                                                     FilterThresholds th, float* __restrict__ stats, int allow_vec) {
+    __shared__ double red[32][kFilterVals];
+    const int r0 = origins[2 * blockIdx.x], c0 = origins[2 * blockIdx.x + 1];
+    if (allow_vec && (c0 & 3) == 0) tile_filter_body<4>(scene, Ci, target, colloc, SH, SW, r0, c0, ps, th, stats, red);
+    else tile_filter_body<1>(scene, Ci, target, colloc, SH, SW, r0, c0, ps, th, stats, red);
+}
 
 // ---------------------------------------------------------------------------------------------- evaluation metrics
 // One CTA per patch, one pass over (pred, gt, mask): the reductions behind masked MAE / MSE / PSNR
 // (Evaluation/DDIM_Multi-step.py:72-95), the global (non-windowed) ssim_simple (:97-101), SAM and ERGAS
 // (Evaluation_Updated/Evaluation_Pure_Generation.py:229-254), finalised by thread 0 in double precision.
+// A thread sums its G pixels x C channels of a step in fp32 and adds the step's partial sums to fp64 accumulators
+// (the fp32 -> fp64 conversion rate, not HBM, bounded the all-fp64 version).
 // out[p][0..7] = mae, mse, psnr, ssim_simple, sam, ergas, valid pixel count, 0.
 constexpr int kMetricsMaxC = 8;
-constexpr int kMetricsThreads = 256;      // 31 double accumulators per thread: keep the register budget wide
+constexpr int kMetricsThreads = 256;
 constexpr int kMetricsOut = 8;
 
-__global__ void __launch_bounds__(kMetricsThreads) patch_metrics_kernel(const float* __restrict__ pred,
+template <int G, int CMAX>
+__global__ void __launch_bounds__(kMetricsThreads, CMAX <= 4 ? 3 : 1) patch_metrics_kernel(const float* __restrict__ pred,
                                                                         const float* __restrict__ gt,
                                                                         const uint8_t* __restrict__ mask, int C, int HW,
                                                                         double* __restrict__ out) {
-    constexpr int kVals = 3 * kMetricsMaxC + 7;          // per channel: sum|d|, sum d^2, sum gt ; then 5 global + count + sam
+    constexpr int kG = 3 * CMAX;                         // per channel: sum|d|, sum d^2, sum gt ; then 5 global + count + sam
+    constexpr int kVals = kG + 7;
     __shared__ double red[32][kVals];
     const int p = blockIdx.x;
     const float* pp = pred + static_cast<size_t>(p) * C * HW;
@@ -241,34 +327,66 @@ __global__ void __launch_bounds__(kMetricsThreads) patch_metrics_kernel(const fl
     double acc[kVals];
 #pragma unroll
     for (int i = 0; i < kVals; ++i) acc[i] = 0.0;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-        const bool w = mp == nullptr || mp[i] != 0;
-        float dot = 0.f, np2 = 0.f, ng2 = 0.f;
+    const int ngroups = HW / G;
+    constexpr int kFlush = G == 4 ? 4 : 1;               // steps (of G pixels) summed in fp32 before the fp64 add
+    for (int ib = threadIdx.x; ib < ngroups; ib += kFlush * blockDim.x) {
+        float part[kVals];
 #pragma unroll
-        for (int c = 0; c < kMetricsMaxC; ++c) {
+        for (int j = 0; j < kVals; ++j) part[j] = 0.f;
+#pragma unroll
+      for (int f = 0; f < kFlush; ++f) {
+        const int i = ib + f * blockDim.x;
+        if (i >= ngroups) break;
+        const int i0 = i * G;
+        bool w[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) w[k] = true;
+        if (mp != nullptr) {
+            uint8_t m[G];
+            ld_b<G>(mp + i0, m);
+#pragma unroll
+            for (int k = 0; k < G; ++k) w[k] = m[k] != 0;
+        }
+        float dot[G], np2[G], ng2[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) dot[k] = np2[k] = ng2[k] = 0.f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
             if (c < C) {
-                const float a = pp[static_cast<size_t>(c) * HW + i], b = gp[static_cast<size_t>(c) * HW + i];
-                const float d = a - b;
-                if (w) {
-                    acc[3 * c] += fabsf(d);
-                    acc[3 * c + 1] += static_cast<double>(d) * d;
+                float av[G], bv[G];
+                ld_f<G>(pp + static_cast<size_t>(c) * HW + i0, av);
+                ld_f<G>(gp + static_cast<size_t>(c) * HW + i0, bv);
+#pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    const float a = av[k], b = bv[k];
+                    const float d = a - b;
+                    if (w[k]) {
+                        part[3 * c] += fabsf(d);
+                        part[3 * c + 1] = fmaf(d, d, part[3 * c + 1]);
+                    }
+                    part[3 * c + 2] += b;
+                    part[kG + 0] += a;
+                    part[kG + 1] += b;
+                    part[kG + 2] = fmaf(a, a, part[kG + 2]);
+                    part[kG + 3] = fmaf(b, b, part[kG + 3]);
+                    part[kG + 4] = fmaf(a, b, part[kG + 4]);
+                    dot[k] = fmaf(a, b, dot[k]);
+                    np2[k] = fmaf(a, a, np2[k]);
+                    ng2[k] = fmaf(b, b, ng2[k]);
                 }
-                acc[3 * c + 2] += b;
-                acc[3 * kMetricsMaxC + 0] += a;
-                acc[3 * kMetricsMaxC + 1] += b;
-                acc[3 * kMetricsMaxC + 2] += static_cast<double>(a) * a;
-                acc[3 * kMetricsMaxC + 3] += static_cast<double>(b) * b;
-                acc[3 * kMetricsMaxC + 4] += static_cast<double>(a) * b;
-                dot = fmaf(a, b, dot);
-                np2 = fmaf(a, a, np2);
-                ng2 = fmaf(b, b, ng2);
             }
         }
-        if (w) {
-            acc[3 * kMetricsMaxC + 5] += 1.0;
-            const float cosv = dot / (fmaxf(sqrtf(np2), 1e-8f) * fmaxf(sqrtf(ng2), 1e-8f));
-            acc[3 * kMetricsMaxC + 6] += acosf(fminf(fmaxf(cosv, -1.f), 1.f));
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            if (w[k]) {
+                part[kG + 5] += 1.f;
+                const float cosv = dot[k] / (fmaxf(sqrtf(np2[k]), 1e-8f) * fmaxf(sqrtf(ng2[k]), 1e-8f));
+                part[kG + 6] += acosf(fminf(fmaxf(cosv, -1.f), 1.f));
+            }
         }
+      }
+#pragma unroll
+        for (int j = 0; j < kVals; ++j) acc[j] += static_cast<double>(part[j]);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -287,7 +405,7 @@ __global__ void __launch_bounds__(kMetricsThreads) patch_metrics_kernel(const fl
     __syncthreads();
     if (threadIdx.x == 0) {
         const double* r = red[0];
-        const double W = r[3 * kMetricsMaxC + 5];
+        const double W = r[kG + 5];
         double sabs = 0.0, ssq = 0.0, eg = 0.0;
         for (int c = 0; c < C; ++c) {
             sabs += r[3 * c];
@@ -298,16 +416,16 @@ __global__ void __launch_bounds__(kMetricsThreads) patch_metrics_kernel(const fl
         }
         const double mae = sabs / (W * C + 1e-8), mse = ssq / (W * C + 1e-8);
         const double n = static_cast<double>(C) * HW;
-        const double mx = r[3 * kMetricsMaxC] / n, my = r[3 * kMetricsMaxC + 1] / n;
-        const double vx = (r[3 * kMetricsMaxC + 2] - n * mx * mx) / (n - 1.0), vy = (r[3 * kMetricsMaxC + 3] - n * my * my) / (n - 1.0);
-        const double cxy = r[3 * kMetricsMaxC + 4] / n - mx * my;
+        const double mx = r[kG] / n, my = r[kG + 1] / n;
+        const double vx = (r[kG + 2] - n * mx * mx) / (n - 1.0), vy = (r[kG + 3] - n * my * my) / (n - 1.0);
+        const double cxy = r[kG + 4] / n - mx * my;
         const double C1 = 0.01 * 0.01, C2 = 0.03 * 0.03;
         double* o = out + static_cast<size_t>(p) * kMetricsOut;
         o[0] = mae;
         o[1] = mse;
         o[2] = mse <= 1e-12 ? 99.0 : 10.0 * log10(1.0 / mse);
         o[3] = ((2 * mx * my + C1) * (2 * cxy + C2)) / ((mx * mx + my * my + C1) * (vx + vy + C2) + 1e-8);
-        o[4] = r[3 * kMetricsMaxC + 6] / W;              // NaN for an empty mask, like torch's mean of nothing
+        o[4] = r[kG + 6] / W;                            // NaN for an empty mask, like torch's mean of nothing
         o[5] = 100.0 * sqrt(eg / C) * 4.0;
         o[6] = W;
         o[7] = 0.0;
@@ -325,42 +443,63 @@ __global__ void stitch_map_kernel(const int32_t* __restrict__ origins, int N, in
     if (i < nrows && j < ncols) grid_map[i * ncols + j] = p;
 }
 
-// One thread per canvas pixel; covering patches visited in ascending (row, col) = ascending patch index.
-__global__ void __launch_bounds__(128) stitch_gather_kernel(const float* __restrict__ preds,
+// One thread per G consecutive canvas pixels of a row (they share their covering patches when stride, ps and x are
+// multiples of G); covering patches visited in ascending (row, col) = ascending patch index, fp32 adds in that order, one
+// fp32 division: no atomics, bit-reproducible, identical for G = 1 and G = 4.
+template <int G, int CMAX>
+__global__ void __launch_bounds__(128, 8) stitch_gather_kernel(const float* __restrict__ preds,
                                                             const int32_t* __restrict__ grid_map, int C, int ps, int stride,
                                                             int nrows, int ncols, int SH, int SW, float* __restrict__ canvas,
                                                             uint8_t* __restrict__ cover) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * G;
     const int y = blockIdx.y;
     if (x >= SW) return;
     const int i_lo = y >= ps ? (y - ps) / stride + 1 : 0;
     const int i_hi = min(nrows - 1, y / stride);
     const int j_lo = x >= ps ? (x - ps) / stride + 1 : 0;
     const int j_hi = min(ncols - 1, x / stride);
-    float acc[kStitchMaxC];
+    float acc[CMAX][G];
 #pragma unroll
-    for (int c = 0; c < kStitchMaxC; ++c) acc[c] = 0.f;
+    for (int c = 0; c < CMAX; ++c)
+#pragma unroll
+        for (int k = 0; k < G; ++k) acc[c][k] = 0.f;
     float cnt = 0.f;
     const size_t pp = static_cast<size_t>(ps) * ps;
     for (int i = i_lo; i <= i_hi; ++i) {
         const int ly = y - i * stride;
+#pragma unroll 4
         for (int j = j_lo; j <= j_hi; ++j) {
-            const int p = grid_map[i * ncols + j];
+            const int p = __ldg(grid_map + i * ncols + j);
             if (p < 0) continue;
             const int lx = x - j * stride;
             const float* src = preds + static_cast<size_t>(p) * C * pp + static_cast<size_t>(ly) * ps + lx;
 #pragma unroll
-            for (int c = 0; c < kStitchMaxC; ++c)
-                if (c < C) acc[c] = __fadd_rn(acc[c], __ldg(src + c * pp));
+            for (int c = 0; c < CMAX; ++c) {
+                if (c < C) {
+                    float v[G];
+                    ld_f<G>(src + c * pp, v);
+#pragma unroll
+                    for (int k = 0; k < G; ++k) acc[c][k] = __fadd_rn(acc[c][k], v[k]);
+                }
+            }
             cnt += 1.f;
         }
     }
     const size_t plane = static_cast<size_t>(SH) * SW;
     const size_t o = static_cast<size_t>(y) * SW + x;
 #pragma unroll
-    for (int c = 0; c < kStitchMaxC; ++c)
-        if (c < C) canvas[c * plane + o] = cnt > 0.f ? __fdiv_rn(acc[c], cnt) : 0.f;
-    cover[o] = cnt > 0.f ? 1 : 0;
+    for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+            float v[G];
+#pragma unroll
+            for (int k = 0; k < G; ++k) v[k] = cnt > 0.f ? __fdiv_rn(acc[c][k], cnt) : 0.f;
+            st_f<G>(canvas + c * plane + o, v);
+        }
+    }
+    uint8_t cv[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) cv[k] = cnt > 0.f ? 1 : 0;
+    st_b<G>(cover + o, cv);
 }
 
 }  // namespace s1s2

@@ -48,6 +48,8 @@ void set_err(std::string* dst, const char* fmt, ...) {
         }                                                                                          \
     } while (0)
 
+inline bool aligned_to(const void* p, size_t a) { return reinterpret_cast<uintptr_t>(p) % a == 0; }
+
 // ---------------------------------------------------------------------------------------------- small kernels
 // Input assembly (replaces t_idx.view.float.repeat + 2x torch.cat, DDIM_Multi-step.py:44-45,131):
 // NCHW f32 -> NHWC16 fp16 pixel record [xlo0..3 | t t 0 0 | c0 c1 c2 c3 | xhi0..3].  x_t rides as an fp16 hi/lo pair
@@ -1052,8 +1054,10 @@ int s1s2_tile_extract(int device, const float* scene, const uint8_t* vmask, int 
     }
     if (N == 0) return S1S2_OK;
     CK(cudaSetDevice(device));
+    const int allow_vec = (SW % 4 == 0 && ps % 4 == 0 && aligned_to(scene, 16) && aligned_to(cond, 16) && aligned_to(mask, 4) &&
+                           (vmask == nullptr || aligned_to(vmask, 4))) ? 1 : 0;
     tile_extract_kernel<<<N, kExtractThreads, 0, static_cast<cudaStream_t>(stream)>>>(scene, vmask, SH, SW, origins, ps, cond,
-                                                                                     mask, valid_ratio);
+                                                                                     mask, valid_ratio, allow_vec);
     CK(cudaGetLastError());
     return S1S2_OK;
 }
@@ -1063,14 +1067,16 @@ int s1s2_tile_filter(int device, const float* scene, int Ci, const float* target
     std::string* err = &g_error;
     if (N == 0) return S1S2_OK;
     if (scene == nullptr || target == nullptr || origins == nullptr || thresholds == nullptr || stats == nullptr || N < 0 ||
-        Ci < 1 || ps < 1 || ps > SH || ps > SW) {
+        Ci < 1 || Ci > kFilterMaxCi || ps < 1 || ps > SH || ps > SW) {
         set_err(err, "s1s2_tile_filter: bad argument (N %d, Ci %d, ps %d, scene %d x %d)", N, Ci, ps, SH, SW);
         return S1S2_ERR_INVALID;
     }
     CK(cudaSetDevice(device));
     FilterThresholds th{thresholds[0], thresholds[1], thresholds[2], thresholds[3], thresholds[4]};
+    const int allow_vec = (SW % 4 == 0 && ps % 4 == 0 && aligned_to(scene, 16) && aligned_to(target, 16) &&
+                           (colloc == nullptr || aligned_to(colloc, 4))) ? 1 : 0;
     tile_filter_kernel<<<N, kFilterThreads, 0, static_cast<cudaStream_t>(stream)>>>(scene, Ci, target, colloc, SH, SW, origins, ps,
-                                                                                   th, stats);
+                                                                                   th, stats, allow_vec);
     CK(cudaGetLastError());
     return S1S2_OK;
 }
@@ -1084,7 +1090,11 @@ int s1s2_patch_metrics(int device, const float* pred, const float* gt, const uin
         return S1S2_ERR_INVALID;
     }
     CK(cudaSetDevice(device));
-    patch_metrics_kernel<<<N, kMetricsThreads, 0, static_cast<cudaStream_t>(stream)>>>(pred, gt, mask, C, HW, out);
+    const bool vec = HW % 4 == 0 && aligned_to(pred, 16) && aligned_to(gt, 16) && (mask == nullptr || aligned_to(mask, 4));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (vec && C <= 4) patch_metrics_kernel<4, 4><<<N, kMetricsThreads, 0, st>>>(pred, gt, mask, C, HW, out);
+    else if (vec) patch_metrics_kernel<4, kMetricsMaxC><<<N, kMetricsThreads, 0, st>>>(pred, gt, mask, C, HW, out);
+    else patch_metrics_kernel<1, kMetricsMaxC><<<N, kMetricsThreads, 0, st>>>(pred, gt, mask, C, HW, out);
     CK(cudaGetLastError());
     return S1S2_OK;
 }
@@ -1100,6 +1110,18 @@ int s1s2_stitch(int device, const float* preds, const int32_t* origins, int N, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(device));
     const int nrows = (SH - ps) / stride + 1, ncols = (SW - ps) / stride + 1;
+    {   // keep the stream-ordered pool's memory across synchronisations (the default threshold of 0 hands it back to the
+        // driver at every sync, which turns the small scratch allocation below into a ~0.5 ms driver call per stitch)
+        static bool pool_set[64] = {};
+        if (device >= 0 && device < 64 && !pool_set[device]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                uint64_t keep = 64ull << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_set[device] = true;
+        }
+    }
     int32_t* grid_map = nullptr;
     CK(cudaMallocAsync(reinterpret_cast<void**>(&grid_map), sizeof(int32_t) * nrows * ncols, st));
     CK(cudaMemsetAsync(grid_map, 0xFF, sizeof(int32_t) * nrows * ncols, st));
@@ -1107,8 +1129,14 @@ int s1s2_stitch(int device, const float* preds, const int32_t* origins, int N, i
         stitch_map_kernel<<<(N + 255) / 256, 256, 0, st>>>(origins, N, stride, nrows, ncols, grid_map);
         CK(cudaGetLastError());
     }
-    dim3 grid((SW + 127) / 128, SH);
-    stitch_gather_kernel<<<grid, 128, 0, st>>>(preds, grid_map, C, ps, stride, nrows, ncols, SH, SW, canvas, cover);
+    if (SW % 4 == 0 && ps % 4 == 0 && stride % 4 == 0 && aligned_to(preds, 16) && aligned_to(canvas, 16) && aligned_to(cover, 4)) {
+        dim3 grid((SW / 4 + 127) / 128, SH);
+        if (C <= 4) stitch_gather_kernel<4, 4><<<grid, 128, 0, st>>>(preds, grid_map, C, ps, stride, nrows, ncols, SH, SW, canvas, cover);
+        else stitch_gather_kernel<4, kStitchMaxC><<<grid, 128, 0, st>>>(preds, grid_map, C, ps, stride, nrows, ncols, SH, SW, canvas, cover);
+    } else {
+        dim3 grid((SW + 127) / 128, SH);
+        stitch_gather_kernel<1, kStitchMaxC><<<grid, 128, 0, st>>>(preds, grid_map, C, ps, stride, nrows, ncols, SH, SW, canvas, cover);
+    }
     CK(cudaGetLastError());
     CK(cudaFreeAsync(grid_map, st));
     return S1S2_OK;

@@ -21,7 +21,10 @@ def patch_metrics(pred, tgt, mask=None):
     tgt = tgt.to(device=pred.device, dtype=torch.float32).contiguous()
     m = None
     if mask is not None:
-        m = (mask.to(pred.device).reshape(N, H * W) > 0).to(torch.uint8).contiguous()
+        m = mask.to(pred.device).reshape(N, H * W)
+        if m.dtype != torch.uint8:                 # tile_extract's u8 masks pass straight through (kernel tests != 0)
+            m = (m > 0).to(torch.uint8)
+        m = m.contiguous()
     out = torch.empty((N, 8), device=pred.device, dtype=torch.float64)
     idx = pred.device.index if pred.device.index is not None else torch.cuda.current_device()
     stream = torch.cuda.current_stream(pred.device).cuda_stream

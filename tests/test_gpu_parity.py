@@ -312,6 +312,42 @@ def test_extract_sample_stitch_roundtrip(env):
     assert float((canvas - truth).abs().max()) <= 1e-6
 
 
+def test_patch_kernels_vector_and_scalar_paths_agree(env):
+    """The patch I/O kernels move float4 / uchar4 when the geometry is 4-element aligned and scalars otherwise.  The same
+    windows embedded one column to the right (unaligned origins and row pitch -> scalar path) must give the same masks,
+    decisions and (to summation-order rounding) the same values; metrics with an odd pixel count and C = 5 take the
+    scalar 8-channel path and are checked against the oracle's definitions."""
+    from s1s2_b200 import metrics, patch
+    dev = env["dev"]
+    rng = np.random.default_rng(11)
+    H, W, ps, st = 96, 128, 32, 16
+    scene = rng.normal(-12, 4, (4, H, W)).astype(np.float32)
+    scene[rng.random((4, H, W)) < 0.02] = np.nan
+    target = rng.random((4, H, W)).astype(np.float32)
+    target[:, :40, :40] *= 0.05                                            # a dark, flat corner: exercises codes 2 / 3
+    org = patch.tile_origins(H, W, ps, st)
+    sc2 = np.full((4, H, W + 3), np.nan, np.float32); sc2[:, :, 1:W + 1] = scene
+    tg2 = np.zeros((4, H, W + 3), np.float32); tg2[:, :, 1:W + 1] = target
+    org2 = org + np.array([0, 1], np.int32)
+    c_a, m_a, r_a = patch.tile_extract(torch.from_numpy(scene).to(dev), org, ps)
+    c_b, m_b, r_b = patch.tile_extract(torch.from_numpy(sc2).to(dev), org2, ps)
+    assert torch.equal(m_a, m_b) and torch.equal(r_a, r_b)
+    assert float((c_a - c_b).abs().max()) <= 1e-6
+    f_a = patch.tile_filter(torch.from_numpy(scene).to(dev), torch.from_numpy(target).to(dev), org, ps).cpu().numpy()
+    f_b = patch.tile_filter(torch.from_numpy(sc2).to(dev), torch.from_numpy(tg2).to(dev), org2, ps).cpu().numpy()
+    assert np.array_equal(f_a[:, 7], f_b[:, 7]) and len(set(f_a[:, 7])) > 1
+    assert np.allclose(f_a[:, :7], f_b[:, :7], rtol=1e-5, atol=1e-9, equal_nan=True)
+    gen = torch.Generator().manual_seed(23)
+    pred, tgt = torch.rand((3, 5, 7, 9), generator=gen), torch.rand((3, 5, 7, 9), generator=gen)
+    mask = (torch.rand((3, 7, 9), generator=gen) > 0.3).float()
+    got = metrics.patch_metrics(pred.to(dev), tgt.to(dev), mask.to(dev)).cpu().numpy()
+    for i in range(3):
+        a, b, mk = pred[i:i + 1], tgt[i:i + 1], mask[i:i + 1]
+        want = [ometrics.masked_mae(a, b, mk), ometrics.masked_mse(a, b, mk), ometrics.psnr(a, b, mk),
+                ometrics.ssim_simple(a, b), ometrics.sam(a, b, mk), ometrics.ergas(a, b, mk)]
+        assert np.allclose(got[i, :6], want, rtol=5e-6, atol=1e-7), (i, got[i], want)
+
+
 # ------------------------------------------------------------------------------------------------ scene + drivers
 def test_scene_pipeline_single_rank(env):
     """extract -> sample -> stitch composed by s1s2_b200.scene equals the pieces run by hand; stitch of the returned

@@ -1,0 +1,106 @@
+"""Achieved HBM GB/s of the patch I/O kernels either side of the sampler (run under gpurun):
+tile_extract, tile_filter, stitch, patch_metrics -- called straight through the C ABI with preallocated device buffers.
+
+For each kernel: ALGORITHMIC bytes (every input byte read once, every output byte written once per window / patch;
+DESIGN.md section 3) divided by the launch duration: K back-to-back launches between one CUDA event pair on the
+launching stream (so the host's enqueue cost is hidden behind the previous launch), L2 flushed (512 MB memset) before
+the first, median of `reps` such measurements.  Working sets: the scene (64 MB + 64 MB target) fits the 126 MB L2 and is
+re-read by overlapping windows by design; predictions / ground truth (841 MiB ... 3.2 GiB) do not.
+Peak = MEASURED_PEAKS.json hbm_gbs.
+
+usage: python tools/hbm_kernels.py [out.json]
+"""
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "s1-to-s2_super-resolution_project-code_b200")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+from s1s2_b200 import _lib, patch, scene as sc  # noqa: E402
+
+K = int(os.environ.get("HBM_K", "8"))          # HBM_K=1 HBM_REPS=1 HBM_STRIDES=64 under ncu
+REPS = int(os.environ.get("HBM_REPS", "7"))
+STRIDES = tuple(int(v) for v in os.environ.get("HBM_STRIDES", "64,32").split(","))
+
+
+def timed(fn, flush, reps=REPS):
+    ts = []
+    for _ in range(reps + 1):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / K)
+    return statistics.median(ts[1:])
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    L = _lib.lib()
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    SH = SW = 2048
+    ps = 256
+    scn = sc.synthetic_scene(SH, SW, seed=0).to(dev).contiguous()
+    g = torch.Generator().manual_seed(7)
+    target = torch.rand((4, SH, SW), generator=g).to(dev)
+    th = (C.c_float * 5)(0.80, 1e-4, 0.10, 0.60, 5e-5)
+    rows = []
+
+    def row(kernel, case, ms, alg, note=None):
+        r = {"kernel": kernel, "case": case, "ms": round(ms, 4), "algorithmic_bytes": alg, "GBps": round(alg / ms / 1e6, 1),
+             "frac_of_hbm_peak": round(alg / ms / 1e6 / peak, 4)}
+        if note:
+            r["note"] = note
+        rows.append(r)
+        print(r, flush=True)
+
+    for stride in STRIDES:
+        org = patch.tile_origins(SH, SW, ps, stride)
+        N = org.shape[0]
+        org_d = torch.as_tensor(org).to(dev)
+        win = 4 * ps * ps * 4
+        cond = torch.empty((N, 4, ps, ps), device=dev)
+        mask = torch.empty((N, ps, ps), device=dev, dtype=torch.uint8)
+        ratio = torch.empty((N,), device=dev)
+        ms = timed(lambda: _lib.check(L.s1s2_tile_extract(0, scn.data_ptr(), None, SH, SW, org_d.data_ptr(), N, ps, cond.data_ptr(),
+                                                          mask.data_ptr(), ratio.data_ptr(), st)), flush)
+        row("tile_extract_kernel", f"2048^2 scene, 256/stride {stride}: {N} windows", ms, N * (2 * win + ps * ps + 4),
+            "bytes per window: 1 MiB read + 1 MiB + 64 KiB written; windows overlap (ps/stride)^2-fold, so most reads are L2 hits "
+            "of the 64 MB scene and the DRAM side is the 1.06 MiB/window write stream")
+        stats = torch.empty((N, 8), device=dev)
+        ms = timed(lambda: _lib.check(L.s1s2_tile_filter(0, scn.data_ptr(), 4, target.data_ptr(), None, SH, SW, org_d.data_ptr(), N,
+                                                         ps, th, stats.data_ptr(), st)), flush)
+        row("tile_filter_kernel", f"{N} windows", ms, N * (2 * win + 32),
+            "bytes per window: scene (validity) + target, 2 MiB read; all L2 hits after the first touch (128 MB working set)")
+        del cond
+        preds = torch.rand((N, 4, ps, ps), generator=g).to(dev)
+        canvas = torch.empty((4, SH, SW), device=dev)
+        cover = torch.empty((SH, SW), device=dev, dtype=torch.uint8)
+        ms = timed(lambda: _lib.check(L.s1s2_stitch(0, preds.data_ptr(), org_d.data_ptr(), N, 4, ps, stride, SH, SW, canvas.data_ptr(),
+                                                    cover.data_ptr(), st)), flush)
+        row("stitch_gather_kernel (+ map kernel, memset)", f"{N} patches -> 4x2048x2048 canvas (stride {stride})", ms,
+            N * win + SH * SW * 17)
+        gt = torch.rand((N, 4, ps, ps), generator=g).to(dev)
+        out = torch.empty((N, 8), device=dev, dtype=torch.float64)
+        ms = timed(lambda: _lib.check(L.s1s2_patch_metrics(0, preds.data_ptr(), gt.data_ptr(), mask.data_ptr(), N, 4, ps * ps,
+                                                           out.data_ptr(), st)), flush)
+        row("patch_metrics_kernel", f"{N} patches", ms, N * (2 * win + ps * ps + 64))
+        del preds, gt
+    res = {"hbm_peak_GBps": peak, "peak_source": "MEASURED_PEAKS.json", "timing": f"{K} back-to-back launches per CUDA event "
+           "pair through the C ABI, L2 flushed before the first, median of 7", "kernels": rows}
+    if len(sys.argv) > 1:
+        open(sys.argv[1], "w").write(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
