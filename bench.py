@@ -5,6 +5,9 @@ A "step" is one complete DDIM-50 sampling (50 fused model calls + scheduler upda
 256x256 patches per GPU.  Workloads (BASELINE.json configs):
   v64   v-prediction UNet, grid B (0..999, 50 entries), eta=0, batch 64 per GPU     [default; north-star target]
   eps16 eps-prediction UNet, grid A (999 -> 0, 50 calls), batch 16 per GPU
+  sweep v-prediction UNet, grid B with 10 / 25 / 50 / 100 / 250 steps (BASELINE config 4, DDIM_Sweep): one JSON line with a
+        `sweep` table of ms per model call and patches/s per step count (`value` = the 50-step row)
+  scene one 4x2048x2048 scene tiled by Patch.py's rule, patch-sharded over the ranks, gathered and stitched (config 5)
 Patches are independent units: N GPUs = N x batch patches per step, no data-path collective ("weak" scaling).
 
   value     patches/s with inputs resident in HBM (CUDA events, barrier + synchronize on both sides, max over ranks)
@@ -252,6 +255,72 @@ def run_scene(args, rank, world, dev):
         dist.destroy_process_group()
 
 
+def run_sweep(args, rank, world, dev):
+    """BASELINE config 4: v-prediction model, grid B from K = 999 with 10 / 25 / 50 / 100 / 250 steps (len(idxs) model calls
+    each, t = 0 included), batch 64 per GPU; per-call latency and patches/s per step count."""
+    import torch
+    import torch.distributed as dist
+    import s1s2_b200
+    from s1s2_b200 import samplers, schedule
+    from oracle import unet as ounet
+    B = args.batch
+    model = s1s2_b200.UNetSmallB200(8, 4, 96, max_batch=B).to(dev)
+    model.load_state_dict(ounet.init_state_dict(8, 4, 96, seed=1235), strict=True)
+    model.eval()
+    _, _, abar = schedule.derive(schedule.cosine_beta_schedule(1000))
+    cond_h, noise_h = synthetic_batch(B, 2024 + rank)
+    cond_d, noise_d = cond_h.to(dev), noise_h.to(dev)
+    init_scale = float(torch.sqrt(1 - abar[999]))
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    table, clocks_all, launches = [], [], 0
+    for n_steps in (10, 25, 50, 100, 250):
+        steps = schedule.steps_grid_b(abar, schedule.grid_b(999, n_steps), "v")
+        reps = max(1, min(args.steps, 500 // len(steps)))
+        for _ in range(max(1, 150 // len(steps))):
+            out = samplers.run_steps(model, steps, cond_d, noise_d, init_scale=init_scale)
+        sync()
+        clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+        l0 = model.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = samplers.run_steps(model, steps, cond_d, noise_d, init_scale=init_scale)
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        launches += int(model.launch_count() - l0)
+        clocks_all.append(clocks.stop())
+        assert bool(torch.isfinite(out).all())
+        table.append({"ddim_steps": n_steps, "model_calls": len(steps), "chains_timed": reps, "ms_per_chain": ms / reps,
+                      "ms_per_model_call": ms / reps / len(steps), "patches_per_s": B * world * reps / (ms / 1e3),
+                      "tflops_per_gpu": FLOP_PER_CALL * len(steps) * B * reps / (ms / 1e3) / 1e12})
+    if rank == 0:
+        peak_tf, _, peak_src = peaks()
+        r50 = next(r for r in table if r["ddim_steps"] == 50)
+        line = {"metric": "DDIM-50 patches/sec", "value": r50["patches_per_s"], "unit": "patches/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r50["ms_per_chain"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (TMEM) and f32 scheduler state",
+                "data": "synthetic", "config": dict(config_block(args, world), workload="DDIM_Sweep (BASELINE config 4): "
+                "v-prediction UNetSmall(8,4,96), grid B from 999 with 10/25/50/100/250 steps, eta=0"),
+                "sweep": table, "gpu_launches": launches, "clocks": clocks_all[2],
+                "roofline": {"bound": "tensor", "achieved": r50["tflops_per_gpu"], "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": r50["tflops_per_gpu"] / peak_tf, "peak_source": peak_src, "traffic": None},
+                "e2e": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def config_block(args, world):
     B = args.batch
     return {"workload": ("DDIM_Multi-step_v_Prediction: v-prediction UNetSmall(8,4,96), grid B 0..999 (50 calls), eta=0"
@@ -269,7 +338,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="v64", choices=["v64", "eps16", "scene"])
+    ap.add_argument("--workload", default="v64", choices=["v64", "eps16", "scene", "sweep"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layers", action="store_true")
@@ -310,6 +379,9 @@ def main():
 
     if args.workload == "scene":
         run_scene(args, rank, world, dev)
+        return
+    if args.workload == "sweep":
+        run_sweep(args, rank, world, dev)
         return
 
     B = args.batch
