@@ -73,6 +73,7 @@ struct ConvParams {
     CUtensorMap tmap_a;
     CUtensorMap tmap_b;
     CUtensorMap tmap_out;         // MODE_STORE / MODE_POOL: NHWC destination, box = 32 channels x the (pooled) pixel tile
+    CUtensorMap tmap_out2;        // MODE_CONVT: tmap_out / tmap_out2 = output rows 2y / 2y+1 as 5-D (c, kx, x, y, n) views
     const float* bias;            // [num_n_tiles * BLOCK_N]
     const uint32_t* amax_in;      // [B] float bits of max|x_t| per patch for this call (nullptr: scale 1)
     __half* out;                  // NHWC fp16 destination (channel offset already applied)
@@ -96,7 +97,7 @@ struct ConvParams {
 // is shifted by (ky*10 + kx) 128-byte rows and whose 8-row-group stride is 10 rows (the hardware applies the 128B
 // swizzle to absolute shared-memory address bits, tools/umma_halo_test.cu).  Activation traffic drops 6.4x.
 constexpr int kHaloW = 10, kHaloH = 18;
-constexpr int kHaloSlots = 3;
+constexpr int kHaloSlotsDefault = 3;
 template <int KBOX>
 struct Halo {                                                   // KBOX channels per pixel row: 128 / 64 / 32-byte rows
     static constexpr int kBytes = kHaloW * kHaloH * KBOX * 2;   // 23040 at KBOX = 64
@@ -132,11 +133,12 @@ __device__ __forceinline__ void philox_normal4(const HeadParams& hp, uint32_t pi
     }
 }
 
-template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, int SBUF = 1, int TPS = 1>
+template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, int SBUF = 1, int TPS = 1,
+          int HSLOTS = kHaloSlotsDefault>
 struct ConvSmem {
     static constexpr int kABox = 128 * KBOX * 2;
     static constexpr int kBBox = (BLOCK_N / CTAS) * KBOX * 2;   // this CTA's share of the weight rows
-    static constexpr int kARing = HALO ? kHaloSlots * Halo<KBOX>::kSlot : 0;
+    static constexpr int kARing = HALO ? HSLOTS * Halo<KBOX>::kSlot : 0;
     static constexpr int kStage = HALO ? TPS * kBBox : BOXES * (kABox + kBBox);   // halo mode: the ring holds weight tiles only
                                                                                   // (TPS taps of one channel chunk per stage)
     // output staging for the TMA store: one [rows][32 channels] fp16 sub-tile (64-byte rows, 64B swizzle) per
@@ -151,6 +153,7 @@ struct ConvSmem {
     static_assert(kStage % 512 == 0 && kBBox % 512 == 0, "stage alignment");
     static_assert(!HALO || (BOXES == 1 && STAGES <= 10), "halo mode");
     static_assert(TPS == 1 || (HALO && (TPS == 3 || TPS == 9)), "taps per stage");
+    static_assert((2 * STAGES + 4 + 2 * HSLOTS) * 8 + 4 <= 256, "barrier block");
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
@@ -187,13 +190,15 @@ __device__ __forceinline__ float range_scale(uint32_t amax_bits, float& s) {
 // WRES (halo mode, one chunk per tap, TPS = 9, one stage): the nine weight tiles are loaded once per CTA and stay
 // resident; the ring then only carries activation halo tiles (inc.0).
 // EPIWG: epilogue warpgroups (warps 4..7 [, 8..11]); with two, each drains half of the accumulator's columns.
+// HSLOTS: depth of the activation halo ring (3; deeper for inc.0, whose 6 KB halo tiles are pure TMA latency).
 template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, bool WRES = false, int SBUF = 1,
-          int TPS = 1, int EPIWG = 1>
+          int TPS = 1, int EPIWG = 1, int HSLOTS = kHaloSlotsDefault>
 __global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(128 + 128 * EPIWG, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
     static_assert(!WRES || (HALO && TPS == 9 && STAGES == 1), "resident weights: halo mode, all nine taps in one stage");
     static_assert(EPIWG == 1 || (EPIWG == 2 && MODE != MODE_HEAD), "epilogue warpgroups");
-    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE, CTAS, HALO, SBUF, TPS>;
+    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE, CTAS, HALO, SBUF, TPS, HSLOTS>;
+    constexpr int kHaloSlots = HSLOTS;            // activation halo ring depth (halo mode)
     constexpr bool kPair = CTAS == 2;
     constexpr bool kTmaStore = (MODE != MODE_HEAD);
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
@@ -233,6 +238,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         tma_prefetch_desc(&p.tmap_a);
         tma_prefetch_desc(&p.tmap_b);
         if constexpr (kTmaStore) tma_prefetch_desc(&p.tmap_out);
+        if constexpr (MODE == MODE_CONVT) tma_prefetch_desc(&p.tmap_out2);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -667,13 +673,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     if (warp == 4 && lane == 0) {
                         const int on0 = tn << (7 - p.tw_log2 - p.th_log2);
                         if constexpr (MODE == MODE_CONVT) {
-                            const int ox0 = 2 * (tx << p.tw_log2), oy0 = 2 * (ty << p.th_log2);
+                            // the 32 columns of a sub-tile belong to one tap (ky, kx): output pixels (2x + kx, 2y + ky) of the
+                            // tile = a plain box of the 5-D view (c, kx, x, y, n) of the output rows of parity ky
+                            const int ix0 = tx << p.tw_log2, iy0 = ty << p.th_log2;
 #pragma unroll
                             for (int c = 0; c < BLOCK_N / 32; ++c) {
                                 const int ng = n_tile * BLOCK_N + c * 32;
                                 const int tap = ng / p.cout;
-                                tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, ng - tap * p.cout, ox0 + (tap & 1),
-                                             oy0 + (tap >> 1), on0);
+                                tma_store_5d((tap >> 1) ? &p.tmap_out2 : &p.tmap_out, sout + c * L::kSubBytes, ng - tap * p.cout,
+                                             tap & 1, ix0, iy0, on0);
                             }
                         } else {
                             const int sh = MODE == MODE_POOL ? 1 : 0;

@@ -170,7 +170,7 @@ CUtensorMapSwizzle swizzle_for(int kbox) {
 }
 
 // ---------------------------------------------------------------------------------------------- layers
-enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_STORE256_1, K_POOL256_1, K_PX_STORE, K_PX_HEAD, K_PX_HEAD32, K_HSTORE, K_HPOOL, K_HSTORE256, K_HPOOL256, K_HINC, K_HC96IN, K_HINC_1WG, K_PX_HEAD32_T1, K_CONVT_2, K_CONVT256_2, K_COUNT };
+enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_PX_STORE, K_PX_HEAD32, K_HSTORE, K_HPOOL, K_HSTORE256, K_HPOOL256, K_HINC, K_HC96IN, K_COUNT };
 
 struct KernelInfo {
     void (*fn)(const ConvParams);
@@ -180,10 +180,10 @@ struct KernelInfo {
 };
 
 template <int BN, int KB, int BX, int ST, int MODE, int CTAS = 2, bool HALO = false, bool WRES = false, int SBUF = 1,
-          int TPS = 1, int EPIWG = 1>
+          int TPS = 1, int EPIWG = 1, int HSLOTS = kHaloSlotsDefault>
 KernelInfo make_kernel() {
     KernelInfo k;
-    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS, HALO, WRES, SBUF, TPS, EPIWG>;
+    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS, HALO, WRES, SBUF, TPS, EPIWG, HSLOTS>;
     k.threads = 128 + 128 * EPIWG;
     k.ctas = CTAS;
     k.px = false;
@@ -191,7 +191,7 @@ KernelInfo make_kernel() {
     k.block_n = BN;
     k.kbox = KB;
     k.boxes = BX;
-    k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS, HALO, SBUF, TPS>::kBytes;
+    k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS, HALO, SBUF, TPS, HSLOTS>::kBytes;
     k.mode = MODE;
     return k;
 }
@@ -232,21 +232,13 @@ const KernelInfo* kernel_table() {
         t[K_HSTORE256] = make_kernel<256, 64, 1, 5, MODE_STORE, 2, true>();
         t[K_HPOOL256] = make_kernel<256, 64, 1, 8, MODE_POOL, 2, true>();
         // Short-K layers: several taps per ring stage (the MMA issue loop costs ~300 cycles per stage: profiles/r1s source view)
-        t[K_HINC] = make_kernel<96, 16, 1, 1, MODE_STORE, 2, true, true, 4, 9, 2>();   // inc.0: 32-byte rows, nine resident weight tiles,
-                                                                                       // 4 staging buffers, two epilogue warpgroups
-        t[K_HINC_1WG] = make_kernel<96, 16, 1, 1, MODE_STORE, 2, true, true, 4, 9, 1>();   // A/B: one epilogue warpgroup
+        t[K_HINC] = make_kernel<96, 16, 1, 1, MODE_STORE, 2, true, true, 4, 9, 2, 8>();   // inc.0: 32-byte rows, nine resident weight
+                                                                  // tiles, 4 staging buffers, two epilogue warpgroups, 8 halo slots
         t[K_HC96IN] = make_kernel<192, 32, 1, 6, MODE_STORE, 2, true, false, 1, 3>();  // down1.0.0: exact K = 96 per tap as three
                                                                                        // 32-channel chunks, one kernel row per stage
         t[K_PX_STORE] = make_px_kernel<64, 5, MODE_STORE>();            // conv1.0: pixels on N (see conv_px.cuh)
-        t[K_PX_HEAD] = make_px_kernel<64, 5, MODE_HEAD>();              // conv1.2 + outc + scheduler, K padded 96 -> 128 per tap
         t[K_PX_HEAD32] = make_px_kernel<32, 4, MODE_HEAD, 3, 3>();        // same with exact 32-channel chunks, one kernel row per
                                                                           // stage, three halo slots (default)
-        t[K_PX_HEAD32_T1] = make_px_kernel<32, 10, MODE_HEAD>();          // A/B: one tap per stage (S1S2_OLD_ISSUE=1)
-        t[K_CONVT_2] = make_kernel<192, 64, 1, 4, MODE_CONVT, 2, false, false, 2, 1, 2>();   // two staging buffers + two epilogue
-        t[K_CONVT256_2] = make_kernel<256, 64, 1, 4, MODE_CONVT, 2, false, false, 1, 1, 2>(); // warpgroups: the transposed convs are
-                                                                                              // epilogue-bound (K = Cin only)
-        t[K_STORE256_1] = make_kernel<256, 64, 1, 3, MODE_STORE, 1>();   // single-CTA variants: A/B measurement only
-        t[K_POOL256_1] = make_kernel<256, 64, 1, 4, MODE_POOL, 1>();     // (S1S2_SINGLE_CTA_256=1)
         t[K_HEAD] = make_kernel<96, 32, 3, 6, MODE_HEAD>();     // conv1.2 + outc + scheduler
         init = true;
     }
@@ -444,23 +436,40 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
             return S1S2_ERR_CUDA;
         }
     }
-    if (k.mode != MODE_HEAD) {
+    if (k.mode == MODE_CONVT) {
+        // destination rows of parity ky as a 5-D view (c, kx, x, y, n) of the double-resolution output: the pixel shuffle
+        // of one tap is then a plain tiled store, box = 32 channels x 1 x the input tile
+        const int Wo = 2 * Wl, Ho = 2 * Hl;
+        const cuuint64_t pb = static_cast<cuuint64_t>(L.dst_pitch) * 2;            // bytes per output pixel
+        cuuint64_t dims[5] = {static_cast<cuuint64_t>(L.cout), 2, static_cast<cuuint64_t>(Wl), static_cast<cuuint64_t>(Hl),
+                              static_cast<cuuint64_t>(h->nalloc)};
+        cuuint64_t strides[4] = {pb, 2 * pb, 2 * Wo * pb, static_cast<cuuint64_t>(Ho) * Wo * pb};
+        cuuint32_t box[5] = {32u, 1u, 1u << g.tw_log2, 1u << g.th_log2, static_cast<cuuint32_t>(g.tn)};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        for (int ky = 0; ky < 2; ++ky) {
+            CUresult r = enc(ky ? &p.tmap_out2 : &p.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, L.dst + static_cast<size_t>(ky) * Wo * L.dst_pitch,
+                             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_err(err, "layer %s: output tensor map (ky %d) rejected (CUresult %d)", L.name, ky, static_cast<int>(r));
+                return S1S2_ERR_CUDA;
+            }
+        }
+    } else if (k.mode != MODE_HEAD) {
         // destination: (C, W, H, N) of the output, box = 32 channels x the output pixels of one M tile, 64B swizzle.
-        //   STORE: same resolution.  POOL: half resolution, box = the pooled tile.  CONVT: double resolution walked
-        //   with element strides (1, 2, 2, 1): one tap's pixels (2x+kx, 2y+ky) of the tile per store.
+        //   STORE: same resolution.  POOL: half resolution, box = the pooled tile.
         const int sh = k.mode == MODE_POOL ? 1 : 0;
-        const int up = k.mode == MODE_CONVT ? 2 : 1;
         if (sh && (g.tw_log2 < 1 || g.th_log2 < 1)) {
             set_err(err, "layer %s: pooled tile needs an M tile at least 2 x 2 pixels", L.name);
             return S1S2_ERR_INVALID;
         }
-        const int Ho = (Hl >> sh) * up, Wo = (Wl >> sh) * up;
+        const int Ho = Hl >> sh, Wo = Wl >> sh;
         cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cout), static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Ho),
                               static_cast<cuuint64_t>(h->nalloc)};
         cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.dst_pitch) * 2, static_cast<cuuint64_t>(Wo) * L.dst_pitch * 2,
                                  static_cast<cuuint64_t>(Ho) * Wo * L.dst_pitch * 2};
-        cuuint32_t box[4] = {32u, ((1u << g.tw_log2) >> sh) * up, ((1u << g.th_log2) >> sh) * up, static_cast<cuuint32_t>(g.tn)};
-        cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(up), static_cast<cuuint32_t>(up), 1};
+        cuuint32_t box[4] = {32u, (1u << g.tw_log2) >> sh, (1u << g.th_log2) >> sh, static_cast<cuuint32_t>(g.tn)};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&p.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, L.dst, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -687,26 +696,7 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     if (getenv("S1S2_NO_PX") == nullptr) {       // default: pixels-on-N kernels for the Cout = 96 full-resolution layers
         for (Layer& L : h->layers) {
             if (L.kid == K_N96) L.kid = K_PX_STORE;
-            if (L.kid == K_HEAD) L.kid = getenv("S1S2_PX_HEAD64") != nullptr ? K_PX_HEAD : K_PX_HEAD32;
-        }
-    }
-    if (getenv("S1S2_OLD_ISSUE") != nullptr) {   // A/B: one tap per stage in the head, one epilogue warpgroup in inc.0
-        for (Layer& L : h->layers) {
-            if (L.kid == K_PX_HEAD32) L.kid = K_PX_HEAD32_T1;
-            if (L.kid == K_HINC) L.kid = K_HINC_1WG;
-        }
-    }
-    if (getenv("S1S2_CONVT_2WG") != nullptr) {   // A/B: two epilogue warpgroups in the transposed convs (measured neutral:
-                                                 // up1 0.312 vs 0.325 ms at batch 64 -- they are not epilogue-compute bound)
-        for (Layer& L : h->layers) {
-            if (L.kid == K_CONVT) L.kid = K_CONVT_2;
-            if (L.kid == K_CONVT256) L.kid = K_CONVT256_2;
-        }
-    }
-    if (getenv("S1S2_SINGLE_CTA_256") != nullptr) {
-        for (Layer& L : h->layers) {
-            if (L.kid == K_STORE256) L.kid = K_STORE256_1;
-            if (L.kid == K_POOL256) L.kid = K_POOL256_1;
+            if (L.kid == K_HEAD) L.kid = K_PX_HEAD32;
         }
     }
     for (Layer& L : h->layers) {
