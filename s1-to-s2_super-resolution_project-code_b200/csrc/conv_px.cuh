@@ -42,7 +42,7 @@ struct PxSmem {
     static constexpr int kBytes = 1024 + kHaloRing + STAGES * kStage + kStaging + kBias + 256;
     static_assert(STAGES >= 2 && STAGES <= 10, "weight ring depth");
     static_assert(TPS == 1 || TPS == 3, "taps per stage");
-    static_assert(HSLOTS == 2 || HSLOTS == 3, "halo ring depth");
+    static_assert(HSLOTS >= 2 && HSLOTS <= 4, "halo ring depth");
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
         // With three halo slots the next halo tile is simply requested before the current chunk's weights (its slot was
         // freed two chunks ago).
         constexpr int kStagesPerChunk = 9 / TPS;
-        constexpr int kIssueStage = HSLOTS >= 3 ? -1 : (STAGES - 1 < kStagesPerChunk - 1 ? STAGES - 1 : kStagesPerChunk - 1);
+        [[maybe_unused]] constexpr int kIssueStage = STAGES - 1 < kStagesPerChunk - 1 ? STAGES - 1 : kStagesPerChunk - 1;
         int s = 0, sh = 0;
         uint32_t ph = 0, phh = 0;
         auto load_halo = [&](int tile, int chunk) {
@@ -134,26 +134,50 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
             if (++sh == kPxHaloSlots) { sh = 0; phh ^= 1; }
         };
         int tile = blockIdx.x, chunk = 0;
-        if (tile < num_tiles) load_halo(tile, 0);
-        while (tile < num_tiles) {
-            int ntile = tile, nchunk = chunk + 1;
-            if (nchunk == p.chunks) { nchunk = 0; ntile += gridDim.x; }
-            if (kIssueStage < 0 && ntile < num_tiles) load_halo(ntile, nchunk);
-            int kcol = chunk * KBOX;
-            for (int st = 0; st < kStagesPerChunk; ++st, kcol += TPS * p.tap_kstride) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                if (elect_one()) {
-                    mbar_expect_tx(&full_bar[s], L::kStage);
+        auto advance = [&](int& t, int& c) { if (++c == p.chunks) { c = 0; t += gridDim.x; } };
+        if constexpr (HSLOTS >= 3) {
+            // the halo cursor runs HSLOTS - 2 positions ahead of the weight stream (its slot was freed two positions earlier)
+            constexpr int kAhead = HSLOTS - 2;
+            int htile = tile, hchunk = 0;
+            for (int d = 0; d < kAhead; ++d)
+                if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
+            while (tile < num_tiles) {
+                if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
+                int kcol = chunk * KBOX;
+                for (int st = 0; st < kStagesPerChunk; ++st, kcol += TPS * p.tap_kstride) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[s], L::kStage);
 #pragma unroll
-                    for (int j = 0; j < TPS; ++j)
-                        tma_load_2d(stage_base + s * L::kStage + j * L::kABox, &p.tmap_b, &full_bar[s], kcol + j * p.tap_kstride, 0);
+                        for (int j = 0; j < TPS; ++j)
+                            tma_load_2d(stage_base + s * L::kStage + j * L::kABox, &p.tmap_b, &full_bar[s], kcol + j * p.tap_kstride, 0);
+                    }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                __syncwarp();
-                if (++s == STAGES) { s = 0; ph ^= 1; }
-                if (st == kIssueStage && ntile < num_tiles) load_halo(ntile, nchunk);
+                advance(tile, chunk);
             }
-            tile = ntile;
-            chunk = nchunk;
+        } else {
+            if (tile < num_tiles) load_halo(tile, 0);
+            while (tile < num_tiles) {
+                int ntile = tile, nchunk = chunk;
+                advance(ntile, nchunk);
+                int kcol = chunk * KBOX;
+                for (int st = 0; st < kStagesPerChunk; ++st, kcol += TPS * p.tap_kstride) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[s], L::kStage);
+#pragma unroll
+                        for (int j = 0; j < TPS; ++j)
+                            tma_load_2d(stage_base + s * L::kStage + j * L::kABox, &p.tmap_b, &full_bar[s], kcol + j * p.tap_kstride, 0);
+                    }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                    if (st == kIssueStage && ntile < num_tiles) load_halo(ntile, nchunk);
+                }
+                tile = ntile;
+                chunk = nchunk;
+            }
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer

@@ -274,8 +274,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     // per instruction and made the single issuing thread the bottleneck (~600 cycles per 4-MMA stage).
     if (HALO && warp == 0) {
         // ================================================================= TMA producer, halo mode (both CTAs)
-        // flat walk over (tile, chunk): the halo tile of the NEXT (tile, chunk) is requested before the nine weight
-        // tiles of the current one, into the slot freed two positions earlier (never blocks on the MMA warp)
+        // flat walk over (tile, chunk) positions: halo tiles are requested ahead of the weight tiles (see kAhead below)
         int s = 0, sa = 0;
         uint32_t ph = 0, pha = 0;
         auto load_halo = [&](int tile, int chunk) {
@@ -304,11 +303,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             }
             __syncwarp();
         }
-        if (tile < num_tiles) load_halo(tile, 0);
+        // the halo cursor runs kAhead = HSLOTS - 2 positions ahead of the weight stream: the slot it targets was freed two
+        // positions earlier, so the request never blocks on the MMA warp while the weight ring still has work queued
+        constexpr int kAhead = kHaloSlots - 2;
+        static_assert(kAhead >= 1, "halo ring depth");
+        int htile = cluster_id, hchunk = 0;
+        auto advance = [&](int& t, int& c) { if (++c == p.chunks) { c = 0; t += num_clusters; } };
+        for (int d = 0; d < kAhead; ++d)
+            if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
         while (tile < num_tiles) {
-            int ntile = tile, nchunk = chunk + 1;
-            if (nchunk == p.chunks) { nchunk = 0; ntile += num_clusters; }
-            if (ntile < num_tiles) load_halo(ntile, nchunk);
+            if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
             const int b_row0 = (tile % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
             int kcol = chunk * KBOX;
             for (int tap = 0; tap < (WRES ? 0 : 9); tap += TPS, kcol += TPS * p.tap_kstride) {
@@ -324,8 +328,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 __syncwarp();
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
-            tile = ntile;
-            chunk = nchunk;
+            advance(tile, chunk);
         }
     } else if (HALO && warp == 1) {
         // ================================================================= MMA issuer, halo mode (leader CTA)
