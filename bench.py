@@ -237,7 +237,7 @@ def run_scene(args, rank, world, dev):
         achieved = value * N_CALLS * FLOP_PER_CALL / 1e12 / world
         line = {"metric": "DDIM-50 patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (TMEM) and f32 scheduler state", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": "Evaluation_Pure_Generation over a whole scene: 4x2048x2048 synthetic Sentinel-1 scene, Patch.py "
                            "tiling 256/stride 64 (841 patches), v-DDIM-50, patch-sharded, NCCL gather to rank 0, overlap-blend stitch",
                            "batch_per_gpu": args.batch, "patches": n, "parallelism": f"patch-sharded x{world}, one gather",
@@ -308,7 +308,7 @@ def run_sweep(args, rank, world, dev):
         r50 = next(r for r in table if r["ddim_steps"] == 50)
         line = {"metric": "DDIM-50 patches/sec", "value": r50["patches_per_s"], "unit": "patches/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r50["ms_per_chain"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (TMEM) and f32 scheduler state",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic", "config": dict(config_block(args, world), workload="DDIM_Sweep (BASELINE config 4): "
                 "v-prediction UNetSmall(8,4,96), grid B from 999 with 10/25/50/100/250 steps, eta=0"),
                 "sweep": table, "gpu_launches": launches, "clocks": clocks_all[2],
@@ -328,6 +328,7 @@ def config_block(args, world):
                          "DDIM_Multi-step / Evaluation_Pure_Generation: eps-prediction UNetSmall(8,4,96), grid A 999->0 (50 calls)"),
             "patch": "4x256x256 cond + 4x256x256 noise (Patch.py shape)", "batch_per_gpu": B, "global_batch": B * world,
             "ddim_steps": 50, "weights": "random init (Models/*.pth absent from the reference tree)",
+            "arithmetic": "f16 operands, f32 accumulate (TMEM), f32 bias / epilogue / scheduler state (x_t carried as an f16 hi/lo pair)",
             "parallelism": f"patch-sharded x{world}, no data-path collective",
             "l2": "working set per step (activation arena ~123 MB/patch) exceeds the 126 MB L2; no flush needed"}
 
@@ -475,7 +476,7 @@ def main():
     if rank == 0:
         line = {"metric": "DDIM-50 patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (TMEM) and f32 scheduler state",
+                "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic", "config": config_block(args, world), "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

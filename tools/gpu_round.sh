@@ -12,9 +12,9 @@ python bench.py --workload sweep --steps 3 --warmup 3 > $O/bench_sweep_$T.json 2
 python bench.py --workload scene --steps 1 --warmup 3 > $O/bench_scene1_$T.json 2>> $O/bench_v64_$T.err; echo "scene rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference_$T.json 2>> $O/bench_v64_$T.err; echo "reference rc=$?"
 python tools/hbm_kernels.py $O/hbm_kernels_$T.json > $O/hbm_kernels_$T.log 2>&1; echo "hbm rc=$?"
-# launch list of the eps16 DDIM-50 bench command (only after it exited 0 without ncu, above)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/launches_$T.csv \
-    python bench.py --workload eps16 --steps 1 --warmup 3 --no-cpu-baseline --no-layers > $O/ncu_launches_$T.log 2>&1; echo "ncu launches rc=$?"
+# launch list of the default bench command (only after it exited 0 without ncu, above): the first 1000 launches
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file $O/launches_$T.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-layers > $O/ncu_launches_$T.log 2>&1; echo "ncu launches rc=$?"
 # one model call at batch 64, every launch with the full set
 python tools/diag.py time 64 2 > $O/diag_time_$T.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:conv_ -s 32 -c 16 -o $O/prof_$T python tools/diag.py time 64 2 > $O/ncu_full_$T.log 2>&1; echo "ncu full rc=$?"
