@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_calls = 4
+    n_calls = 10
     cpu_oracle_sample(args.workload, 1, threads)                       # page in torch / oneDNN
     for _ in range(args.warmup):
         cpu_oracle_sample(args.workload, 1, threads)
@@ -468,10 +468,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cpu_oracle_sample(args.workload, 1, threads)
-        n_calls = 10
+        n_calls = N_CALLS
         dt, pps = cpu_oracle_sample(args.workload, n_calls, threads)
         cpu = {"value": pps, "unit": "patches/s", "cores": threads, "kind": "port",
-               "sample": f"{n_calls} of the 50 model calls of one patch ({dt:.1f} s), oracle/ fp32 PyTorch CPU, extrapolated x5"}
+               "sample": f"one complete DDIM-50 chain (all {n_calls} model calls + scheduler updates) of one 256x256 patch "
+                         f"({dt:.1f} s), oracle/ fp32 PyTorch CPU, {threads} threads"}
 
     if rank == 0:
         line = {"metric": "DDIM-50 patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,

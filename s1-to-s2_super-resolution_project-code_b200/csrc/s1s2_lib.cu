@@ -212,10 +212,9 @@ KernelInfo make_px_kernel() {
     return k;
 }
 
-const KernelInfo* kernel_table() {
-    static KernelInfo t[K_COUNT];
-    static bool init = false;
-    if (!init) {
+struct KernelTable {
+    KernelInfo t[K_COUNT];
+    KernelTable() {
         // UMMA time per instruction is ~128 cycles (one M row per cycle) whatever N <= 256 is, so N = 256 tiles are
         // used wherever the GEMM N (Cout, or 4*Cout for the transposed convs) is a multiple of 256.
         t[K_INC] = make_kernel<96, 16, 3, 4, MODE_STORE>();     // Cin = 16-channel pixel record
@@ -231,7 +230,7 @@ const KernelInfo* kernel_table() {
         t[K_HPOOL] = make_kernel<192, 64, 1, 10, MODE_POOL, 2, true>();
         t[K_HSTORE256] = make_kernel<256, 64, 1, 5, MODE_STORE, 2, true>();
         t[K_HPOOL256] = make_kernel<256, 64, 1, 8, MODE_POOL, 2, true>();
-        // Short-K layers: several taps per ring stage (the MMA issue loop costs ~300 cycles per stage: profiles/r1s source view)
+        // Short-K layers: several taps per ring stage (the MMA issue loop costs ~300 cycles per stage: ncu source view)
         t[K_HINC] = make_kernel<96, 16, 1, 1, MODE_STORE, 2, true, true, 4, 9, 2, 8>();   // inc.0: 32-byte rows, nine resident weight
                                                                   // tiles, 4 staging buffers, two epilogue warpgroups, 8 halo slots
         t[K_HC96IN] = make_kernel<192, 32, 1, 6, MODE_STORE, 2, true, false, 1, 3>();  // down1.0.0: exact K = 96 per tap as three
@@ -240,9 +239,11 @@ const KernelInfo* kernel_table() {
         t[K_PX_HEAD32] = make_px_kernel<32, 4, MODE_HEAD, 3, 3>();        // same with exact 32-channel chunks, one kernel row per
                                                                           // stage, three halo slots (default)
         t[K_HEAD] = make_kernel<96, 32, 3, 6, MODE_HEAD>();     // conv1.2 + outc + scheduler
-        init = true;
     }
-    return t;
+};
+const KernelInfo* kernel_table() {
+    static const KernelTable table;        // function-local static: initialised once, thread-safe (C++11)
+    return table.t;
 }
 
 struct Layer {
