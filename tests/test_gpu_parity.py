@@ -251,6 +251,29 @@ def test_full_size_batch_properties(env):
     assert torch.equal(y1[0], y[2])
 
 
+def test_max_batch_64_matches_batch_1(env):
+    """BASELINE config 3's batch (64 patches of 256x256, the largest single-GPU configuration): every patch of the batch
+    equals the same patch sampled alone (bit-exact), phantom tiles and the last partial cluster wave included."""
+    import s1s2_b200
+    from s1s2_b200 import samplers, schedule
+    dev = env["dev"]
+    big = s1s2_b200.UNetSmallB200(8, 4, 96, max_batch=64).to(dev)
+    big.load_state_dict(env["sd"], strict=True)
+    big.eval()
+    x, cond = _inputs(64, 256, 256, seed=77)
+    ab = env["abar"]
+    steps = schedule.steps_grid_b(ab, schedule.grid_b(999, 2), "v")
+    s = float(torch.sqrt(1 - ab[999]))
+    y = samplers.run_steps(big, steps, cond.to(dev), x.to(dev), init_scale=s).clone()
+    assert torch.isfinite(y).all() and float(y.min()) >= 0.0 and float(y.max()) <= 1.0
+    for k in (0, 31, 63):
+        y1 = samplers.run_steps(big, steps, cond[k:k + 1].to(dev), x[k:k + 1].to(dev), init_scale=s)
+        assert torch.equal(y1[0], y[k]), k
+    y61 = samplers.run_steps(big, steps, cond[:61].to(dev), x[:61].to(dev), init_scale=s)      # odd batch: phantom tiles
+    assert torch.equal(y61, y[:61])
+    del big
+
+
 # ------------------------------------------------------------------------------------------------ patch I/O
 def test_tile_extract_matches_golden(env):
     from s1s2_b200 import patch
