@@ -126,9 +126,11 @@ int s1s2_stitch(int device, const float* preds, const int32_t* origins, int N, i
 
 /* Evaluation metrics of N predicted patches in one pass each (the drivers' per-file metric calls:
  * masked_mae / masked_mse / psnr / ssim_simple, Evaluation/DDIM_Multi-step.py:72-101; sam / ergas,
- * Evaluation_Updated/Evaluation_Pure_Generation.py:229-254).
+ * Evaluation_Updated/Evaluation_Pure_Generation.py:229-254) plus the per-channel error sums behind the dataset-level
+ * pixel-weighted aggregation of the batched evaluators (channelwise_error_sums, Evaluation/Limitation_Test.py:118-133).
  *   pred, gt f32[N,C,HW] device; mask u8[N,HW] device or NULL (all valid); C <= 8
- *   out f64[N,8] device: mae, mse, psnr, ssim_simple, sam, ergas, valid-pixel count, 0 */
+ *   out f64[N,24] device: [0..7] mae, mse, psnr, ssim_simple, sam, ergas, valid-pixel count, 0;
+ *                         [8+c] sum |pred-gt| and [16+c] sum (pred-gt)^2 of channel c over the valid pixels (0 for c >= C) */
 int s1s2_patch_metrics(int device, const float* pred, const float* gt, const uint8_t* mask, int N, int C, int HW,
                        double* out, void* stream);
 

@@ -36,14 +36,44 @@ def sd_to_np(sd, prefix="sd/"):
     return {prefix + k: v.detach().numpy() for k, v in sd.items()}
 
 
+def gen_metrics_agg(lt, out_dir):
+    """Dataset-level, pixel-weighted aggregation of Limitation_Test.py:118-159: channelwise_error_sums over three
+    batches (masked, unmasked, one empty mask row) accumulated the way run_eval does (:330-334), then aggregate_final
+    with equal and with explicit band weights."""
+    g = torch.Generator().manual_seed(31)
+    out = {}
+    abs_tot, sq_tot, w_tot = torch.zeros(4), torch.zeros(4), torch.zeros(())
+    for b, (B, masked) in enumerate(((3, True), (2, False), (2, True))):
+        pred, tgt = torch.rand(B, 4, 24, 20, generator=g), torch.rand(B, 4, 24, 20, generator=g)
+        mask = (torch.rand(B, 24, 20, generator=g) > 0.25).float() if masked else None
+        if b == 2:
+            mask[1] = 0.0                                  # a patch without a single valid pixel
+        a, q, w = lt.channelwise_error_sums(pred, tgt, mask)
+        out[f"agg/pred{b}"], out[f"agg/tgt{b}"] = pred.numpy(), tgt.numpy()
+        if mask is not None:
+            out[f"agg/mask{b}"] = mask.numpy()
+        out[f"agg/abs{b}"], out[f"agg/sq{b}"], out[f"agg/w{b}"] = a.numpy(), q.numpy(), w.numpy()
+        abs_tot += a; sq_tot += q; w_tot += w
+    for tag, bw in (("eq", None), ("bw", [1.0, 1.0, 1.0, 2.0])):
+        mae, mse, ps, mae_c, mse_c, ps_c = lt.aggregate_final(abs_tot, sq_tot, w_tot, bw)
+        out[f"agg/final_{tag}"] = np.array([mae, mse, ps], np.float64)
+        out[f"agg/final_{tag}_c"] = np.stack([mae_c, mse_c, ps_c]).astype(np.float64)
+    np.savez_compressed(os.path.join(out_dir, "metrics_agg.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "tests", "golden"))
+    ap.add_argument("--only", default=None, choices=[None, "metrics_agg"], help="write just this fixture file")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     torch.set_num_threads(1)           # one summation order, reproducible fixtures
     torch.use_deterministic_algorithms(True)
+    if args.only == "metrics_agg":
+        gen_metrics_agg(load_ref(args.ref, "Evaluation/Limitation_Test.py", "ref_lt"), args.out)
+        print("metrics_agg.npz", os.path.getsize(os.path.join(args.out, "metrics_agg.npz")))
+        return
 
     if "rasterio" not in sys.modules:  # Patch.py imports rasterio at module scope; only raster I/O uses it
         sys.modules["rasterio"] = types.ModuleType("rasterio")
@@ -251,6 +281,7 @@ def main():
     out["filt/mask"] = M_all.astype(np.uint8); out["filt/ps_stride"] = np.array([ps, st], np.int32)
     out["filt/rows"] = np.array(rows, np.float64)      # row, col, code, valid_ratio, var0..3, dark_fraction, laplacian_var
     np.savez_compressed(os.path.join(args.out, "filters.npz"), **out)
+    gen_metrics_agg(lt, args.out)
 
     for f in sorted(os.listdir(args.out)):
         print(f, os.path.getsize(os.path.join(args.out, f)))

@@ -2,7 +2,8 @@
 
 Restates ``masked_mse`` / ``masked_mae`` / ``psnr`` / ``ssim_simple`` -- Evaluation/DDIM_Multi-step.py:72-101
 (the reference's SSIM is global, not windowed), ``sam`` / ``ergas`` --
-Evaluation_Updated/Evaluation_Pure_Generation.py:229-254.
+Evaluation_Updated/Evaluation_Pure_Generation.py:229-254, and the dataset-level pixel-weighted aggregation
+``channelwise_error_sums`` / ``aggregate_final`` -- Evaluation/Limitation_Test.py:118-159.
 """
 import math
 
@@ -53,3 +54,28 @@ def ergas(pred, tgt, mask=None, scale_ratio: float = 4.0) -> float:
         rmse = math.sqrt(max(masked_mse(pred[:, c:c + 1], tgt[:, c:c + 1], mask), 0.0))
         acc += (rmse / (tgt[:, c:c + 1].mean().item() + 1e-8)) ** 2
     return 100.0 * (acc / C) ** 0.5 * scale_ratio
+
+
+def channelwise_error_sums(pred, tgt, mask=None):
+    """Per-channel sums of |pred - tgt| and (pred - tgt)^2 over the valid pixels of a batch, and the number of valid
+    pixels (Limitation_Test.py:118-133).  Returns (abs_sum[C], sq_sum[C], valid_pixels) as fp32 tensors."""
+    w = _w(pred, mask)
+    d = pred - tgt
+    return (w * d.abs()).sum(dim=(0, 2, 3)), (w * d ** 2).sum(dim=(0, 2, 3)), w.sum()
+
+
+def aggregate_final(abs_sum_c, sq_sum_c, w_pix_sum, band_weights=None):
+    """Dataset-level MAE / MSE / PSNR from sums accumulated over all batches (Limitation_Test.py:135-159): per-channel
+    means over the valid pixels, combined with equal or normalised band weights; PSNR = 99 when MSE <= 1e-12.
+    Returns (mae, mse, psnr, mae_c, mse_c, psnr_c)."""
+    n = w_pix_sum.clamp_min(1e-8)
+    mae_c, mse_c = abs_sum_c / n, sq_sum_c / n
+    if band_weights is None:
+        mae, mse = mae_c.mean().item(), mse_c.mean().item()
+    else:
+        bw = torch.tensor(band_weights, dtype=mae_c.dtype)
+        bw = bw / bw.sum().clamp_min(1e-8)
+        mae, mse = (mae_c * bw).sum().item(), (mse_c * bw).sum().item()
+    ps = 99.0 if mse <= 1e-12 else 10.0 * math.log10(1.0 / mse)
+    ps_c = torch.where(mse_c <= 1e-12, torch.full_like(mse_c, 99.0), 10.0 * torch.log10(1.0 / mse_c))
+    return mae, mse, ps, mae_c.numpy(), mse_c.numpy(), ps_c.numpy()

@@ -307,10 +307,12 @@ __global__ void __launch_bounds__(kFilterThreads, 4) tile_filter_kernel(const fl
 // (Evaluation_Updated/Evaluation_Pure_Generation.py:229-254), finalised by thread 0 in double precision.
 // A thread sums its G pixels x C channels of a step in fp32 and adds the step's partial sums to fp64 accumulators
 // (the fp32 -> fp64 conversion rate, not HBM, bounded the all-fp64 version).
-// out[p][0..7] = mae, mse, psnr, ssim_simple, sam, ergas, valid pixel count, 0.
+// out[p][0..7] = mae, mse, psnr, ssim_simple, sam, ergas, valid pixel count, 0;
+// out[p][8 + c] = sum |pred - gt| and out[p][16 + c] = sum (pred - gt)^2 of channel c over the patch's valid pixels: the
+// per-batch sums of the dataset-level, pixel-weighted aggregation (Evaluation/Limitation_Test.py:118-133).
 constexpr int kMetricsMaxC = 8;
 constexpr int kMetricsThreads = 256;
-constexpr int kMetricsOut = 8;
+constexpr int kMetricsOut = 8 + 2 * kMetricsMaxC;
 
 template <int G, int CMAX>
 __global__ void __launch_bounds__(kMetricsThreads, CMAX <= 4 ? 3 : 1) patch_metrics_kernel(const float* __restrict__ pred,
@@ -429,6 +431,10 @@ __global__ void __launch_bounds__(kMetricsThreads, CMAX <= 4 ? 3 : 1) patch_metr
         o[5] = 100.0 * sqrt(eg / C) * 4.0;
         o[6] = W;
         o[7] = 0.0;
+        for (int c = 0; c < kMetricsMaxC; ++c) {
+            o[8 + c] = c < C ? r[3 * c] : 0.0;
+            o[8 + kMetricsMaxC + c] = c < C ? r[3 * c + 1] : 0.0;
+        }
     }
 }
 

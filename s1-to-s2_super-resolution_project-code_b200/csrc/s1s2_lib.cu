@@ -564,7 +564,7 @@ int check_batch(s1s2_handle* h, int B) {
 // ================================================================================================ C ABI
 extern "C" {
 
-int s1s2_abi_version(void) { return 1; }
+int s1s2_abi_version(void) { return 2; }   // 2: s1s2_patch_metrics rows grew from 8 to 24 doubles (per-channel sums)
 
 const char* s1s2_global_error(void) { return g_error.c_str(); }
 const char* s1s2_last_error(const s1s2_handle* h) { return h != nullptr ? h->err.c_str() : g_error.c_str(); }

@@ -9,10 +9,11 @@ import torch
 METRIC_NAMES = ("mae", "mse", "psnr", "ssim_simple", "sam", "ergas", "valid")
 
 
-def patch_metrics(pred, tgt, mask=None):
-    """All six metrics of N patches in one fused CUDA pass each (s1s2_patch_metrics): f64[N,7] in METRIC_NAMES order.
-    pred, tgt f32[N,C,H,W] on the same CUDA device; mask [N,H,W] / [N,1,H,W] (non-zero = valid) or None.
-    One device->host copy of the result replaces ~10 `.item()` synchronisations per patch of the reference drivers."""
+METRIC_ROW = 24        # doubles per patch written by s1s2_patch_metrics (include/s1s2_b200.h)
+
+
+def _patch_metrics_raw(pred, tgt, mask=None):
+    """f64[N,24] rows of s1s2_patch_metrics: one fused CUDA pass per patch over (pred, tgt, mask)."""
     from . import _lib
     if pred.device.type != "cuda":
         raise _lib.S1S2Error("patch_metrics runs on a CUDA device only (no CPU fallback)")
@@ -25,12 +26,44 @@ def patch_metrics(pred, tgt, mask=None):
         if m.dtype != torch.uint8:                 # tile_extract's u8 masks pass straight through (kernel tests != 0)
             m = (m > 0).to(torch.uint8)
         m = m.contiguous()
-    out = torch.empty((N, 8), device=pred.device, dtype=torch.float64)
+    out = torch.empty((N, METRIC_ROW), device=pred.device, dtype=torch.float64)
     idx = pred.device.index if pred.device.index is not None else torch.cuda.current_device()
     stream = torch.cuda.current_stream(pred.device).cuda_stream
     _lib.check(_lib.lib().s1s2_patch_metrics(idx, pred.data_ptr(), tgt.data_ptr(), m.data_ptr() if m is not None else None,
                                              N, Cn, H * W, out.data_ptr(), C.c_void_p(stream)))
-    return out[:, :7]
+    return out
+
+
+def patch_metrics(pred, tgt, mask=None):
+    """All six metrics of N patches in one fused CUDA pass each (s1s2_patch_metrics): f64[N,7] in METRIC_NAMES order.
+    pred, tgt f32[N,C,H,W] on the same CUDA device; mask [N,H,W] / [N,1,H,W] (non-zero = valid) or None.
+    One device->host copy of the result replaces ~10 `.item()` synchronisations per patch of the reference drivers."""
+    return _patch_metrics_raw(pred, tgt, mask)[:, :7]
+
+
+def channelwise_error_sums(pred, tgt, mask=None):
+    """Limitation_Test.py:118-133 on the device: (abs_sum[C], sq_sum[C], valid_pixels) of a batch as float64 CUDA
+    tensors -- add them up over the batches of a dataset and hand the totals to ``aggregate_final``."""
+    raw = _patch_metrics_raw(pred, tgt, mask)
+    Cn = pred.shape[1]
+    return raw[:, 8:8 + Cn].sum(0), raw[:, 16:16 + Cn].sum(0), raw[:, 6].sum()
+
+
+def aggregate_final(abs_sum_c, sq_sum_c, w_pix_sum, band_weights=None):
+    """Limitation_Test.py:135-159: dataset-level MAE / MSE / PSNR from the accumulated sums: per-channel means over the
+    valid pixels, combined with equal or normalised band weights.  Returns (mae, mse, psnr, mae_c, mse_c, psnr_c)."""
+    a, q = abs_sum_c.detach().double().cpu(), sq_sum_c.detach().double().cpu()
+    n = torch.as_tensor(w_pix_sum).detach().double().cpu().clamp_min(1e-8)
+    mae_c, mse_c = a / n, q / n
+    if band_weights is None:
+        mae, mse = float(mae_c.mean()), float(mse_c.mean())
+    else:
+        bw = torch.tensor(band_weights, dtype=torch.float64)
+        bw = bw / bw.sum().clamp_min(1e-8)
+        mae, mse = float((mae_c * bw).sum()), float((mse_c * bw).sum())
+    ps = 99.0 if mse <= 1e-12 else 10.0 * math.log10(1.0 / mse)
+    ps_c = torch.where(mse_c <= 1e-12, torch.full_like(mse_c, 99.0), 10.0 * torch.log10(1.0 / mse_c))
+    return mae, mse, ps, mae_c.numpy(), mse_c.numpy(), ps_c.numpy()
 
 
 def _weights(pred, mask):

@@ -459,6 +459,26 @@ def test_fused_patch_metrics_match_oracle(env):
     assert identical[0, 2] == 99.0 and identical[0, 0] == 0.0          # psnr's mse <= 1e-12 branch
 
 
+def test_pixel_weighted_aggregation_matches_golden(env):
+    """metrics.channelwise_error_sums / aggregate_final (per-channel sums from the fused metrics kernel) vs the values
+    Limitation_Test.py:118-159 produced (tests/golden/metrics_agg.npz): three batches accumulated like run_eval does.
+    fp64 sums vs torch fp32 sums: 2e-6 relative."""
+    from s1s2_b200 import metrics
+    z = np.load(os.path.join(G, "metrics_agg.npz"))
+    dev = env["dev"]
+    tot = None
+    for b in range(3):
+        mask = torch.from_numpy(z[f"agg/mask{b}"]).to(dev) if f"agg/mask{b}" in z.files else None
+        a, q, w = metrics.channelwise_error_sums(torch.from_numpy(z[f"agg/pred{b}"]).to(dev), torch.from_numpy(z[f"agg/tgt{b}"]).to(dev), mask)
+        assert np.allclose(a.cpu().numpy(), z[f"agg/abs{b}"], rtol=2e-6) and np.allclose(q.cpu().numpy(), z[f"agg/sq{b}"], rtol=2e-6)
+        assert float(w) == float(z[f"agg/w{b}"])
+        tot = (a, q, w) if tot is None else (tot[0] + a, tot[1] + q, tot[2] + w)
+    for tag, bw in (("eq", None), ("bw", [1.0, 1.0, 1.0, 2.0])):
+        mae, mse, ps, mae_c, mse_c, ps_c = metrics.aggregate_final(*tot, bw)
+        assert np.allclose([mae, mse, ps], z[f"agg/final_{tag}"], rtol=2e-6)
+        assert np.allclose(np.stack([mae_c, mse_c, ps_c]), z[f"agg/final_{tag}_c"], rtol=2e-6)
+
+
 def test_quality_filters_match_golden(env):
     """s1s2_tile_filter vs values the reference's own Patch.py functions produced (tests/golden/filters.npz): decision
     codes exact, statistics within 1e-4 relative (fp64 one-pass sums vs numpy float32 pairwise sums)."""

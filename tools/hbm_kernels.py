@@ -91,10 +91,10 @@ def main():
         row("stitch_gather_kernel (+ map kernel, memset)", f"{N} patches -> 4x2048x2048 canvas (stride {stride})", ms,
             N * win + SH * SW * 17)
         gt = torch.rand((N, 4, ps, ps), generator=g).to(dev)
-        out = torch.empty((N, 8), device=dev, dtype=torch.float64)
+        out = torch.empty((N, 24), device=dev, dtype=torch.float64)
         ms = timed(lambda: _lib.check(L.s1s2_patch_metrics(0, preds.data_ptr(), gt.data_ptr(), mask.data_ptr(), N, 4, ps * ps,
                                                            out.data_ptr(), st)), flush)
-        row("patch_metrics_kernel", f"{N} patches", ms, N * (2 * win + ps * ps + 64))
+        row("patch_metrics_kernel", f"{N} patches", ms, N * (2 * win + ps * ps + 192))
         del preds, gt
     res = {"hbm_peak_GBps": peak, "peak_source": "MEASURED_PEAKS.json", "timing": f"{K} back-to-back launches per CUDA event "
            "pair through the C ABI, L2 flushed before the first, median of 7", "kernels": rows}
