@@ -6,6 +6,9 @@
   python -m s1s2_b200.drivers ddim_sweep   ...   Evaluation/DDIM_Sweep.py --mode ddim_sweep (:387-416); --param v sweeps the
                                                  step counts of BASELINE.json's config 4 on the v model
   python -m s1s2_b200.drivers true_infer   ...   Evaluation_Updated/Evaluation_Pure_Generation.py --mode ddim --true_infer (:539-574)
+  python -m s1s2_b200.drivers limitation   ...   Evaluation/Limitation_Test.py run_eval (:273-400) and, with --param v,
+                                                 Limitation_Test_v_Prediction.py run_eval (:258-372): batched DDPM / DDIM
+                                                 sampling, dataset-level pixel-weighted MAE / MSE / PSNR, *_pred.npy / *_gt.npy
   python -m s1s2_b200.drivers scene        ...   whole-scene generation (Patch.py tiling + stitch, s1s2_b200.scene), under torchrun
 
 Same flag names (--patch_dir --ckpt --out_dir --T --base_ch --max_files --t_start --ddim_steps --ddim_eta --t_small
@@ -185,6 +188,64 @@ def cmd_true_infer(args):
     print("[DONE] DDIM (TRUE-INFER)")
 
 
+def cmd_limitation(args):
+    """run_eval of Limitation_Test.py (:273-400, eps) / Limitation_Test_v_Prediction.py (:258-372, v): --mode ddpm|ddim,
+    --time_schedule cosine|linear, --batch_size, --band_weights, --partial_reverse_k (eps), --save_n; prints the reference's
+    report (equal-channel, optional band-weighted, per-channel, all pixel-weighted over the whole dataset) and also writes it
+    to limitation_summary.txt.  PNG previews are not produced."""
+    os.makedirs(args.out_dir, exist_ok=True)
+    device = torch.device("cuda")
+    torch.manual_seed(args.seed)
+    files = _files(args)
+    _, x_gt0, _, Cc, Ct = load_npz_as_tensors(os.path.join(args.patch_dir, files[0]), device)
+    print(f"[INFO] inputs={Cc}, target={Ct}")
+    args.batch = args.batch_size
+    model = load_model(args.ckpt, Cc + Ct, Ct, args.base_ch, device, args.batch_size)
+    betas = schedule.make_schedule(args.T, args.time_schedule)
+    betas, alphas, alpha_bar = schedule.derive(betas)
+    betas, alphas, alpha_bar = betas.to(device), alphas.to(device), alpha_bar.to(device)
+    tot, saved, lines = None, 0, []
+    for bi, (lo, names, cond, gt, mask) in enumerate(_batches(args, files, device)):
+        if args.param == "v":
+            if args.mode == "ddpm":
+                x_pred = samplers.sample_ddpm_v(model, cond, betas, alphas, alpha_bar, Ct, seed=args.seed + bi)
+            else:
+                x_pred = samplers.sample_ddim_v(model, cond, alpha_bar, Ct, steps=args.ddim_steps, eta=args.ddim_eta,
+                                                t_start=args.lim_t_start, seed=args.seed + bi)
+        elif args.mode == "ddpm":
+            x_pred = samplers.ddpm_sample(model, cond, betas, alphas, alpha_bar, Ct, seed=args.seed + bi)
+        else:
+            x_pred = samplers.ddim_sample(model, cond, alphas, alpha_bar, Ct, steps=args.ddim_steps)
+        mk = None if any(m is None for m in mask) else torch.cat(mask, 0)
+        sums = metrics.channelwise_error_sums(x_pred, gt, mk)
+        tot = sums if tot is None else tuple(a + b for a, b in zip(tot, sums))
+        for b in range(len(names)):
+            if saved >= args.save_n:
+                break
+            stem = f"{args.mode}_{bi:04d}_{b:02d}"
+            np.save(os.path.join(args.out_dir, f"{stem}_pred.npy"), x_pred[b].cpu().numpy())
+            np.save(os.path.join(args.out_dir, f"{stem}_gt.npy"), gt[b].cpu().numpy())
+            saved += 1
+        if args.partial_reverse_k and bi == 0 and args.param == "eps":
+            for k in args.partial_reverse_k:
+                xr = samplers.partial_ddim_from_gt(model, gt, cond, alpha_bar, int(k))
+                mae_k, mse_k, ps_k, _, _, _ = metrics.aggregate_final(*metrics.channelwise_error_sums(xr, gt, mk))
+                lines.append(f"[partial-reverse k={k}] MAE={mae_k:.6f}  MSE={mse_k:.6f}  PSNR={ps_k:.3f} dB")
+    mae, mse, ps, mae_c, mse_c, ps_c = metrics.aggregate_final(*tot)
+    lines += ["", "==== Unweighted (equal-channel) ====", f"MAE:  {mae:.6f}", f"MSE:  {mse:.6f}", f"PSNR: {ps:.3f} dB"]
+    if args.band_weights:
+        mae_w, mse_w, ps_w, _, _, _ = metrics.aggregate_final(*tot, band_weights=args.band_weights)
+        lines += ["", "==== Weighted (band_weights) ====", f"band_weights = {args.band_weights}", f"MAE_w:  {mae_w:.6f}",
+                  f"MSE_w:  {mse_w:.6f}", f"PSNR_w: {ps_w:.3f} dB"]
+    bands = ["B2", "B3", "B4", "B8"] if len(mae_c) == 4 else [f"Band{i}" for i in range(len(mae_c))]
+    lines += ["", "-- Per-channel metrics (pixel-weighted) --"]
+    lines += [f"{nm:>3s}:  MAE={mae_c[i]:.6f}  MSE={mse_c[i]:.6f}  PSNR={ps_c[i]:.3f} dB" for i, nm in enumerate(bands)]
+    print("\n".join(lines))
+    with open(os.path.join(args.out_dir, "limitation_summary.txt"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print(f"\n[INFO] Results saved to: {args.out_dir}")
+
+
 def cmd_onestep(args):
     os.makedirs(args.out_dir, exist_ok=True)
     device = torch.device("cuda")
@@ -247,7 +308,7 @@ def cmd_scene(args):
 
 def main(argv=None):
     ap = argparse.ArgumentParser("s1s2_b200 drivers")
-    ap.add_argument("cmd", choices=["onestep", "ddim", "ddim_v", "ddim_sweep", "true_infer", "scene"])
+    ap.add_argument("cmd", choices=["onestep", "ddim", "ddim_v", "ddim_sweep", "true_infer", "limitation", "scene"])
     ap.add_argument("--patch_dir")
     ap.add_argument("--ckpt")
     ap.add_argument("--out_dir", required=True)
@@ -263,6 +324,15 @@ def main(argv=None):
     ap.add_argument("--t_start_grid", default="300,200,150,100")
     ap.add_argument("--ddim_steps_grid", default="10,20,50,100")
     ap.add_argument("--true_infer", action="store_true")
+    # Limitation_Test*.py flags (the v script's --t_start is --lim_t_start here: default None = start from T-1)
+    ap.add_argument("--mode", default="ddim", choices=["ddpm", "ddim"])
+    ap.add_argument("--time_schedule", default="cosine", choices=["cosine", "linear"])
+    ap.add_argument("--batch_size", type=int, default=2)
+    ap.add_argument("--save_n", type=int, default=16)
+    ap.add_argument("--band_weights", nargs="*", type=float, default=None)
+    ap.add_argument("--partial_reverse_k", nargs="*", type=int, default=None)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--lim_t_start", type=int, default=None)
     # additions
     ap.add_argument("--param", default="eps", choices=["eps", "v"])
     ap.add_argument("--batch", type=int, default=16)
@@ -282,6 +352,8 @@ def main(argv=None):
         cmd_sweep(args)
     elif args.cmd == "true_infer":
         cmd_true_infer(args)
+    elif args.cmd == "limitation":
+        cmd_limitation(args)
     else:
         cmd_scene(args)
 

@@ -429,6 +429,27 @@ def test_drivers_write_reference_outputs(env, tmp_path):
     a = list(__import__("csv").reader(open(odir / "f" / "ddim_sweep_summary.csv")))[1][:7]
     b = list(__import__("csv").reader(open(odir / "g" / "ddim_sweep_summary.csv")))[1][:7]
     assert a == b
+    # Limitation_Test.py run_eval: batched DDIM, dataset-level pixel-weighted report; the report must equal the oracle's
+    # aggregation (Limitation_Test.py:118-159) of the predictions the driver saved
+    lim = ["--patch_dir", str(pdir), "--ckpt", str(ckpt), "--batch_size", "2", "--save_n", "16"]
+    drivers.main(["limitation", "--out_dir", str(odir / "h"), "--mode", "ddim", "--ddim_steps", "3", "--band_weights", "1", "1", "1",
+                  "2", "--partial_reverse_k", "2"] + lim)
+    txt = open(odir / "h" / "limitation_summary.txt").read()
+    assert "==== Unweighted (equal-channel) ====" in txt and "==== Weighted (band_weights) ====" in txt and "[partial-reverse k=2]" in txt
+    tot = None
+    for i in range(5):
+        d = np.load(pdir / f"patch_{i:06d}.npz")
+        pred = torch.from_numpy(np.load(odir / "h" / f"ddim_{i // 2:04d}_{i % 2:02d}_pred.npy"))[None]
+        gt = torch.from_numpy(np.load(odir / "h" / f"ddim_{i // 2:04d}_{i % 2:02d}_gt.npy"))[None]
+        assert np.array_equal(gt[0].numpy(), d["target"])
+        sums = ometrics.channelwise_error_sums(pred, gt, torch.from_numpy(d["mask"].astype(np.float32))[None])
+        tot = sums if tot is None else tuple(a_ + b_ for a_, b_ in zip(tot, sums))
+    mae, mse, ps, mae_c, _, _ = ometrics.aggregate_final(*tot)
+    assert f"MAE:  {mae:.6f}" in txt and f"MSE:  {mse:.6f}" in txt and f"PSNR: {ps:.3f} dB" in txt
+    assert f" B8:  MAE={mae_c[3]:.6f}" in txt
+    # the v script's run_eval in DDPM mode (in-kernel noise), short schedule
+    drivers.main(["limitation", "--out_dir", str(odir / "i"), "--mode", "ddpm", "--param", "v", "--T", "16"] + lim)
+    assert (odir / "i" / "ddpm_0002_00_pred.npy").exists() and "-- Per-channel metrics (pixel-weighted) --" in open(odir / "i" / "limitation_summary.txt").read()
 
 
 def test_fused_patch_metrics_match_oracle(env):
