@@ -66,14 +66,38 @@ def _setup(args):
     return device, files, model, alpha_bar.to(device)
 
 
-def _batches(args, files, device):
-    for lo in range(0, len(files), args.batch):
+def _load_cpu(path):
+    """The arrays of one patch file as CPU tensors (same conversions as load_npz_as_tensors)."""
+    d = np.load(path)
+    cond = torch.from_numpy(np.nan_to_num(d["inputs"].astype(np.float32))).unsqueeze(0)
+    gt = torch.from_numpy(np.nan_to_num(d["target"].astype(np.float32))).unsqueeze(0)
+    mask = torch.from_numpy(np.nan_to_num(d["mask"].astype(np.float32))).unsqueeze(0) if "mask" in d else None
+    return cond, gt, mask
+
+
+def _batches(args, files, device, workers=4):
+    """Batches of `args.batch` patch files as device tensors.  The files of the NEXT batch are read and decompressed by a
+    small thread pool (and staged in pinned memory) while the caller samples the current one, so file I/O -- ~5 ms per
+    compressed 256x256 patch, a third of a DDIM-50 batch if done serially -- stays off the GPU's critical path."""
+    from concurrent.futures import ThreadPoolExecutor
+    pin = device.type == "cuda"
+
+    def load(lo):
         names = files[lo:lo + args.batch]
-        items = [load_npz_as_tensors(os.path.join(args.patch_dir, f), device) for f in names]
-        cond = torch.cat([it[0] for it in items], 0)
-        gt = torch.cat([it[1] for it in items], 0)
-        mask = [it[2] for it in items]
-        yield lo, names, cond, gt, mask
+        items = [_load_cpu(os.path.join(args.patch_dir, f)) for f in names]
+        cond, gt = torch.cat([it[0] for it in items], 0), torch.cat([it[1] for it in items], 0)
+        if pin:
+            cond, gt = cond.pin_memory(), gt.pin_memory()
+        return lo, names, cond, gt, [it[2] for it in items]
+
+    starts = list(range(0, len(files), args.batch))
+    with ThreadPoolExecutor(max_workers=1) as pool:          # one batch ahead; np.load / zlib release the GIL
+        nxt = pool.submit(load, starts[0]) if starts else None
+        for k in range(len(starts)):
+            lo, names, cond, gt, mask = nxt.result()
+            nxt = pool.submit(load, starts[k + 1]) if k + 1 < len(starts) else None
+            yield (lo, names, cond.to(device, non_blocking=True), gt.to(device, non_blocking=True),
+                   [m.to(device) if m is not None else None for m in mask])
 
 
 def _mstd(a):

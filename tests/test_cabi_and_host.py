@@ -109,3 +109,31 @@ def test_tiling_and_sharding_host_logic():
             assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_driver_batches_prefetch_keeps_order_and_contents(tmp_path):
+    """drivers._batches reads the next batch in a background thread; order, grouping and contents must be those of a
+    plain serial read (Evaluation/DDIM_Multi-step.py:104-111 conversions)."""
+    import types
+    import numpy as np
+    import torch
+    from s1s2_b200 import drivers
+    rng = np.random.default_rng(5)
+    for i in range(7):
+        x = rng.normal(size=(4, 8, 8)).astype(np.float32)
+        x[0, 0, 0] = np.nan
+        kw = dict(inputs=x, target=rng.random((4, 8, 8)).astype(np.float32))
+        if i != 3:
+            kw["mask"] = (rng.random((8, 8)) > 0.2).astype(np.uint8)
+        np.savez_compressed(tmp_path / f"patch_{i:06d}.npz", **kw)
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz"))
+    args = types.SimpleNamespace(patch_dir=str(tmp_path), batch=3)
+    seen = []
+    for lo, names, cond, gt, mask in drivers._batches(args, files, torch.device("cpu")):
+        assert names == files[lo:lo + 3] and cond.shape[0] == len(names) == len(mask)
+        for j, f in enumerate(names):
+            c, g, m, _, _ = drivers.load_npz_as_tensors(os.path.join(tmp_path, f), torch.device("cpu"))
+            assert torch.equal(cond[j:j + 1], c) and torch.equal(gt[j:j + 1], g) and not torch.isnan(cond).any()
+            assert (m is None and mask[j] is None) or torch.equal(mask[j], m)
+        seen += names
+    assert seen == files
