@@ -47,7 +47,7 @@ def _inputs(B, H, W, seed=0):
 
 
 # ------------------------------------------------------------------------------------------------ denoiser
-@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 64, 64), (1, 48, 80), (1, 256, 256)])
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 64, 64), (1, 48, 80), (1, 256, 256), (3, 16, 16), (2, 128, 384)])
 def test_layers_isolated(env, B, H, W):
     from layer_ref import check_layers
     x, cond = _inputs(B, H, W, seed=B * 1000 + H)
