@@ -47,7 +47,7 @@ struct PxSmem {
 };
 
 // 384 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 and 8-11 two epilogue
-// warpgroups.  The epilogue is the long pole of these layers (transposition through shared memory, and for the head a
+// warpgroups.  The epilogue is a long pole of these layers (transposition through shared memory, and for the head a
 // second pass with global loads), so the two TMEM accumulators are drained by different warpgroups: group g owns
 // accumulator g, staging buffer g and named barrier 1+g and handles every other tile of the CTA.
 constexpr int kPxThreads = 384;

@@ -18,9 +18,13 @@
 // CTAs' shared memory and write both CTAs' TMEM.  Halving the weight traffic per SM is what lifts the kernel off
 // the shared-memory bandwidth bound the single-CTA version sat on (profiles/r1a_*: 62-66 % tensor-pipe active).
 //
-// Warp roles (256 threads per CTA): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM
-// allocator, warps 4..7 = epilogue (TMEM lane quadrant = warp_idx % 4).  Two TMEM accumulators so the epilogue of
-// tile i overlaps the MMAs of tile i+1.
+// Warp roles (256 threads per CTA, 384 with a second epilogue warpgroup): warp 0 = TMA producer, warp 1 = MMA issuer
+// (leader CTA only), warp 2 = TMEM allocator, warps 4..7 [and 8..11] = epilogue (TMEM lane quadrant = warp_idx % 4).
+// Two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Halo mode (every 3x3 layer): the activations of a (tile, channel chunk) are ONE halo tile that all nine taps read
+// through shifted UMMA descriptors; the ring then streams weight tiles only, TPS taps per stage (see the kernel's
+// template notes for TPS / WRES / EPIWG / HSLOTS and the measurements behind them).
 //
 // Dynamic range: activations are fp16, the reference is fp32.  Every model call carries a per-patch power-of-two
 // scale s = 2^k derived from max|x_t| (k = 0 while max|x_t| < 16): the first layer stores relu(.)/s, every later
