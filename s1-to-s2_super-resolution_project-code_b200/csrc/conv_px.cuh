@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();                    // see conv_umma_kernel: the prologue above overlaps the previous kernel's tail
+    pdl_wait();
 
     if (warp == 0) {
         // ================================================================= TMA producer

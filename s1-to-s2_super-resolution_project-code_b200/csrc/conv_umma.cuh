@@ -273,6 +273,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     if constexpr (kPair) cluster_sync_all();    // peer's barriers are initialised before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Everything above touched only shared memory, TMEM and constant data (tensor maps, bias): under programmatic dependent
+    // launch it overlaps the previous kernel's tail.  Activations, amax and the sampler state are read / written below.
+    pdl_launch_dependents();
+    pdl_wait();
 
     // Both issue loops below run WARP-UNIFORM (all 32 lanes wait on the barriers and keep the loop state; one
     // elected lane issues TMA / MMA / commit).  Uniform control flow lets ptxas keep descriptors and addresses in

@@ -113,6 +113,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel of the stream may start being scheduled (its CTAs still need this grid's SMs to
+// drain); wait: every memory operation of the prerequisite grid is complete and visible.  Both are no-ops when the
+// kernel was launched without the programmatic-stream-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- CTA pair (cluster of 2) helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

@@ -499,6 +499,24 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
     return S1S2_OK;
 }
 
+// Launch with programmatic stream serialization: the kernel may be scheduled while its predecessor in the stream drains;
+// it orders itself behind the predecessor's memory operations with griddepcontrol.wait (S1S2_NO_PDL=1: plain launches).
+int launch_conv(const KernelInfo& k, int grid, const ConvParams& p, cudaStream_t st, std::string* err) {
+    static const bool pdl = getenv("S1S2_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(k.threads);
+    cfg.dynamicSmemBytes = k.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, k.fn, p));
+    return S1S2_OK;
+}
+
 int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, cudaStream_t st, std::string* err) {
     const KernelInfo& k = kernel_table()[L.kid];
     ConvParams& p = L.p;
@@ -506,8 +524,8 @@ int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, cudaS
         p.B = B;
         p.amax_in = amax_in;
         const int tiles = (p.W >> 3) * ((p.H + 31) >> 5) * B;
-        k.fn<<<tiles < h->num_sms ? tiles : h->num_sms, kPxThreads, k.smem, st>>>(p);
-        CK(cudaGetLastError());
+        int rc = launch_conv(k, tiles < h->num_sms ? tiles : h->num_sms, p, st, err);
+        if (rc != S1S2_OK) return rc;
         ++h->launches;
         return S1S2_OK;
     }
@@ -517,8 +535,8 @@ int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, cudaS
     p.amax_in = amax_in;
     const int group_tiles = ((p.num_m_tiles + k.ctas - 1) / k.ctas) * p.num_n_tiles;   // one CTA group per (ctas M tiles, 1 N tile)
     const int clusters = group_tiles < h->num_sms / k.ctas ? group_tiles : h->num_sms / k.ctas;
-    k.fn<<<k.ctas * clusters, k.threads, k.smem, st>>>(p);                 // __cluster_dims__(ctas, 1, 1)
-    CK(cudaGetLastError());
+    int rc = launch_conv(k, k.ctas * clusters, p, st, err);                // __cluster_dims__(ctas, 1, 1)
+    if (rc != S1S2_OK) return rc;
     ++h->launches;
     return S1S2_OK;
 }
