@@ -12,6 +12,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "ptx_sm100.cuh"
+
 namespace s1s2 {
 
 constexpr int kExtractThreads = 1024;
@@ -314,6 +316,41 @@ constexpr int kMetricsMaxC = 8;
 constexpr int kMetricsThreads = 256;
 constexpr int kMetricsOut = 8 + 2 * kMetricsMaxC;
 
+// Thread 0's finalisation of the block-reduced sums r[0 .. 3*CMAX+7) into one output row (shared by both kernels).
+template <int CMAX>
+__device__ __forceinline__ void metrics_finalize(const double* r, int C, int HW, double* o) {
+    constexpr int kG = 3 * CMAX;
+    const double W = r[kG + 5];
+    double sabs = 0.0, ssq = 0.0, eg = 0.0;
+    for (int c = 0; c < C; ++c) {
+        sabs += r[3 * c];
+        ssq += r[3 * c + 1];
+        const double rmse = sqrt(fmax(r[3 * c + 1] / (W + 1e-8), 0.0));
+        const double q = rmse / (r[3 * c + 2] / HW + 1e-8);
+        eg += q * q;
+    }
+    const double mae = sabs / (W * C + 1e-8), mse = ssq / (W * C + 1e-8);
+    const double n = static_cast<double>(C) * HW;
+    double sum_b = 0.0;                              // global sum of gt = sum of the per-channel sums
+    for (int c = 0; c < C; ++c) sum_b += r[3 * c + 2];
+    const double mx = r[kG] / n, my = sum_b / n;
+    const double vx = (r[kG + 2] - n * mx * mx) / (n - 1.0), vy = (r[kG + 3] - n * my * my) / (n - 1.0);
+    const double cxy = r[kG + 4] / n - mx * my;
+    const double C1 = 0.01 * 0.01, C2 = 0.03 * 0.03;
+    o[0] = mae;
+    o[1] = mse;
+    o[2] = mse <= 1e-12 ? 99.0 : 10.0 * log10(1.0 / mse);
+    o[3] = ((2 * mx * my + C1) * (2 * cxy + C2)) / ((mx * mx + my * my + C1) * (vx + vy + C2) + 1e-8);
+    o[4] = r[kG + 6] / W;                            // NaN for an empty mask, like torch's mean of nothing
+    o[5] = 100.0 * sqrt(eg / C) * 4.0;
+    o[6] = W;
+    o[7] = 0.0;
+    for (int c = 0; c < kMetricsMaxC; ++c) {
+        o[8 + c] = c < C ? r[3 * c] : 0.0;
+        o[8 + kMetricsMaxC + c] = c < C ? r[3 * c + 1] : 0.0;
+    }
+}
+
 template <int G, int CMAX>
 __global__ void __launch_bounds__(kMetricsThreads, CMAX <= 4 ? 3 : 1) patch_metrics_kernel(const float* __restrict__ pred,
                                                                         const float* __restrict__ gt,
@@ -349,9 +386,10 @@ __global__ void __launch_bounds__(kMetricsThreads, CMAX <= 4 ? 3 : 1) patch_metr
 #pragma unroll
             for (int k = 0; k < G; ++k) w[k] = m[k] != 0;
         }
-        float dot[G], np2[G], ng2[G];
+        // per pixel: sum_c a, a.b, |a|^2, |b|^2 over the channels (they feed both the global ssim_simple sums and SAM)
+        float sa[G], dot[G], np2[G], ng2[G];
 #pragma unroll
-        for (int k = 0; k < G; ++k) dot[k] = np2[k] = ng2[k] = 0.f;
+        for (int k = 0; k < G; ++k) sa[k] = dot[k] = np2[k] = ng2[k] = 0.f;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
             if (c < C) {
@@ -367,11 +405,7 @@ __global__ void __launch_bounds__(kMetricsThreads, CMAX <= 4 ? 3 : 1) patch_metr
                         part[3 * c + 1] = fmaf(d, d, part[3 * c + 1]);
                     }
                     part[3 * c + 2] += b;
-                    part[kG + 0] += a;
-                    part[kG + 1] += b;
-                    part[kG + 2] = fmaf(a, a, part[kG + 2]);
-                    part[kG + 3] = fmaf(b, b, part[kG + 3]);
-                    part[kG + 4] = fmaf(a, b, part[kG + 4]);
+                    sa[k] += a;
                     dot[k] = fmaf(a, b, dot[k]);
                     np2[k] = fmaf(a, a, np2[k]);
                     ng2[k] = fmaf(b, b, ng2[k]);
@@ -380,6 +414,10 @@ __global__ void __launch_bounds__(kMetricsThreads, CMAX <= 4 ? 3 : 1) patch_metr
         }
 #pragma unroll
         for (int k = 0; k < G; ++k) {
+            part[kG + 0] += sa[k];
+            part[kG + 2] += np2[k];
+            part[kG + 3] += ng2[k];
+            part[kG + 4] += dot[k];
             if (w[k]) {
                 part[kG + 5] += 1.f;
                 const float cosv = dot[k] / (fmaxf(sqrtf(np2[k]), 1e-8f) * fmaxf(sqrtf(ng2[k]), 1e-8f));
@@ -405,37 +443,145 @@ __global__ void __launch_bounds__(kMetricsThreads, CMAX <= 4 ? 3 : 1) patch_metr
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) metrics_finalize<CMAX>(red[0], C, HW, out + static_cast<size_t>(p) * kMetricsOut);
+}
+
+// Streaming version for the usual geometry (C <= 4, HW a multiple of kMsChunk, 16-byte aligned planes): the planes of a
+// patch are contiguous, so one elected thread streams them through a ring of shared-memory stages with 1-D bulk copies
+// (cp.async.bulk + mbarrier transaction counts: no tensor map, loads fully asynchronous and as deep as the ring), and 16
+// consumer warps reduce from shared memory.  The register-path kernel above is bound by load latency at 24 warps per SM
+// (ncu: issue 42 %, DRAM 41 %); here memory and math overlap by construction.  Same arithmetic, same output rows.
+constexpr int kMsChunk = 2048;                      // pixels per stage
+constexpr int kMsStages = 3;                        // 3 x 66 KB of the 227 KB
+constexpr int kMsConsumers = 512;                   // 4 pixels (one float4 per plane) per consumer thread per stage
+constexpr int kMsThreads = kMsConsumers + 32;       // + one producer warp
+constexpr int kMsC = 4;
+constexpr int kMsStageBytes = 2 * kMsC * kMsChunk * 4 + kMsChunk;      // pred + gt planes, mask bytes
+constexpr int kMsSmemBytes = kMsStages * kMsStageBytes + 64;
+
+__global__ void __launch_bounds__(kMsThreads, 1) patch_metrics_stream_kernel(const float* __restrict__ pred,
+                                                                             const float* __restrict__ gt,
+                                                                             const uint8_t* __restrict__ mask, int C, int HW,
+                                                                             double* __restrict__ out) {
+    constexpr int CMAX = kMsC;
+    constexpr int kG = 3 * CMAX;
+    constexpr int kVals = kG + 7;
+    extern __shared__ __align__(128) uint8_t ms_smem[];
+    __shared__ double red[32][kVals];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ms_smem + kMsStages * kMsStageBytes);
+    uint64_t* empty_bar = full_bar + kMsStages;
+    const int p = blockIdx.x;
+    const float* pp = pred + static_cast<size_t>(p) * C * HW;
+    const float* gp = gt + static_cast<size_t>(p) * C * HW;
+    const uint8_t* mp = mask != nullptr ? mask + static_cast<size_t>(p) * HW : nullptr;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = HW / kMsChunk;
     if (threadIdx.x == 0) {
-        const double* r = red[0];
-        const double W = r[kG + 5];
-        double sabs = 0.0, ssq = 0.0, eg = 0.0;
-        for (int c = 0; c < C; ++c) {
-            sabs += r[3 * c];
-            ssq += r[3 * c + 1];
-            const double rmse = sqrt(fmax(r[3 * c + 1] / (W + 1e-8), 0.0));
-            const double q = rmse / (r[3 * c + 2] / HW + 1e-8);
-            eg += q * q;
+        for (int s = 0; s < kMsStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kMsConsumers / 32);       // one arrive per consumer warp
         }
-        const double mae = sabs / (W * C + 1e-8), mse = ssq / (W * C + 1e-8);
-        const double n = static_cast<double>(C) * HW;
-        const double mx = r[kG] / n, my = r[kG + 1] / n;
-        const double vx = (r[kG + 2] - n * mx * mx) / (n - 1.0), vy = (r[kG + 3] - n * my * my) / (n - 1.0);
-        const double cxy = r[kG + 4] / n - mx * my;
-        const double C1 = 0.01 * 0.01, C2 = 0.03 * 0.03;
-        double* o = out + static_cast<size_t>(p) * kMetricsOut;
-        o[0] = mae;
-        o[1] = mse;
-        o[2] = mse <= 1e-12 ? 99.0 : 10.0 * log10(1.0 / mse);
-        o[3] = ((2 * mx * my + C1) * (2 * cxy + C2)) / ((mx * mx + my * my + C1) * (vx + vy + C2) + 1e-8);
-        o[4] = r[kG + 6] / W;                            // NaN for an empty mask, like torch's mean of nothing
-        o[5] = 100.0 * sqrt(eg / C) * 4.0;
-        o[6] = W;
-        o[7] = 0.0;
-        for (int c = 0; c < kMetricsMaxC; ++c) {
-            o[8 + c] = c < C ? r[3 * c] : 0.0;
-            o[8 + kMetricsMaxC + c] = c < C ? r[3 * c + 1] : 0.0;
+        mbar_fence_init();
+    }
+    __syncthreads();
+    double acc[kVals];
+#pragma unroll
+    for (int i = 0; i < kVals; ++i) acc[i] = 0.0;
+    if (warp == kMsConsumers / 32) {
+        // ---------------------------------------------------------------- producer warp
+        int s = 0;
+        uint32_t ph = 0;
+        const uint32_t bytes = static_cast<uint32_t>(2 * C * kMsChunk * 4 + (mp != nullptr ? kMsChunk : 0));
+        for (int ch = 0; ch < nchunks; ++ch) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (lane == 0) {
+                uint8_t* st = ms_smem + s * kMsStageBytes;
+                mbar_expect_tx(&full_bar[s], bytes);
+                for (int c = 0; c < C; ++c) {
+                    bulk_load_1d(st + c * kMsChunk * 4, pp + static_cast<size_t>(c) * HW + ch * kMsChunk, kMsChunk * 4, &full_bar[s]);
+                    bulk_load_1d(st + (CMAX + c) * kMsChunk * 4, gp + static_cast<size_t>(c) * HW + ch * kMsChunk, kMsChunk * 4,
+                                 &full_bar[s]);
+                }
+                if (mp != nullptr) bulk_load_1d(st + 2 * CMAX * kMsChunk * 4, mp + ch * kMsChunk, kMsChunk, &full_bar[s]);
+            }
+            __syncwarp();
+            if (++s == kMsStages) { s = 0; ph ^= 1; }
+        }
+    } else {
+        // ---------------------------------------------------------------- consumers: 4 pixels per thread per stage
+        int s = 0;
+        uint32_t ph = 0;
+        float part[kVals];
+#pragma unroll
+        for (int j = 0; j < kVals; ++j) part[j] = 0.f;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            mbar_wait(&full_bar[s], ph);
+            const uint8_t* st = ms_smem + s * kMsStageBytes;
+            bool w[4] = {true, true, true, true};
+            if (mp != nullptr) {
+                const uchar4 m = *reinterpret_cast<const uchar4*>(st + 2 * CMAX * kMsChunk * 4 + threadIdx.x * 4);
+                w[0] = m.x != 0; w[1] = m.y != 0; w[2] = m.z != 0; w[3] = m.w != 0;
+            }
+            float sa[4] = {0.f, 0.f, 0.f, 0.f}, dot[4] = {0.f, 0.f, 0.f, 0.f}, np2[4] = {0.f, 0.f, 0.f, 0.f}, ng2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) {
+                if (c < C) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(st + c * kMsChunk * 4 + threadIdx.x * 16);
+                    const float4 b4 = *reinterpret_cast<const float4*>(st + (CMAX + c) * kMsChunk * 4 + threadIdx.x * 16);
+                    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float a = av[k], b = bv[k];
+                        const float d = a - b;
+                        if (w[k]) {
+                            part[3 * c] += fabsf(d);
+                            part[3 * c + 1] = fmaf(d, d, part[3 * c + 1]);
+                        }
+                        part[3 * c + 2] += b;
+                        sa[k] += a;
+                        dot[k] = fmaf(a, b, dot[k]);
+                        np2[k] = fmaf(a, a, np2[k]);
+                        ng2[k] = fmaf(b, b, ng2[k]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);           // this warp's reads of the stage are in registers
+            if (++s == kMsStages) { s = 0; ph ^= 1; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                part[kG + 0] += sa[k];
+                part[kG + 2] += np2[k];
+                part[kG + 3] += ng2[k];
+                part[kG + 4] += dot[k];
+                if (w[k]) {
+                    part[kG + 5] += 1.f;
+                    const float cosv = dot[k] / (fmaxf(sqrtf(np2[k]), 1e-8f) * fmaxf(sqrtf(ng2[k]), 1e-8f));
+                    part[kG + 6] += acosf(fminf(fmaxf(cosv, -1.f), 1.f));
+                }
+            }
+            if ((ch & 3) == 3 || ch == nchunks - 1) {            // fold the fp32 partial sums (<= 16 pixels) into fp64
+#pragma unroll
+                for (int j = 0; j < kVals; ++j) { acc[j] += static_cast<double>(part[j]); part[j] = 0.f; }
+            }
         }
     }
+    // block reduction (the producer warp contributes zeros) and finalisation: identical to patch_metrics_kernel
+#pragma unroll
+    for (int i = 0; i < kVals; ++i) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < kVals; ++i) {
+            const double v = warp_sum(lane < (kMsThreads >> 5) ? red[lane][i] : 0.0);
+            if (lane == 0) red[0][i] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) metrics_finalize<CMAX>(red[0], C, HW, out + static_cast<size_t>(p) * kMetricsOut);
 }
 
 // grid_map[(row/stride) * ncols + col/stride] = patch index (entries stay -1 where no patch was kept).

@@ -1101,7 +1101,17 @@ int s1s2_patch_metrics(int device, const float* pred, const float* gt, const uin
     CK(cudaSetDevice(device));
     const bool vec = HW % 4 == 0 && aligned_to(pred, 16) && aligned_to(gt, 16) && (mask == nullptr || aligned_to(mask, 4));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (vec && C <= 4) patch_metrics_kernel<4, 4><<<N, kMetricsThreads, 0, st>>>(pred, gt, mask, C, HW, out);
+    const bool stream_ok = vec && C <= kMsC && HW % kMsChunk == 0 && (mask == nullptr || aligned_to(mask, 16)) &&
+                           getenv("S1S2_METRICS_REGPATH") == nullptr;
+    if (stream_ok) {                   // bulk-copy ring + 16 consumer warps (the usual 256 x 256 x 4 geometry)
+        static bool attr_set[64] = {};                         // per device (the attribute lives in the device's context)
+        if (device < 0 || device >= 64 || !attr_set[device]) {
+            CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(patch_metrics_stream_kernel),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytes));
+            if (device >= 0 && device < 64) attr_set[device] = true;
+        }
+        patch_metrics_stream_kernel<<<N, kMsThreads, kMsSmemBytes, st>>>(pred, gt, mask, C, HW, out);
+    } else if (vec && C <= 4) patch_metrics_kernel<4, 4><<<N, kMetricsThreads, 0, st>>>(pred, gt, mask, C, HW, out);
     else if (vec) patch_metrics_kernel<4, kMetricsMaxC><<<N, kMetricsThreads, 0, st>>>(pred, gt, mask, C, HW, out);
     else patch_metrics_kernel<1, kMetricsMaxC><<<N, kMetricsThreads, 0, st>>>(pred, gt, mask, C, HW, out);
     CK(cudaGetLastError());
