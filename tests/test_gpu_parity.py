@@ -173,6 +173,18 @@ def test_eps_ddim_grid_a_teacher_forced(env):
     _teacher_forced(env, schedule.steps_eps_grid_a(env["abar"], 200, 5), cond, x)
 
 
+def test_eps_ddim50_config2_teacher_forced_full_size(env):
+    """BASELINE config 2 at full size: eps-prediction DDIM-50 on grid A from t = 999 (Evaluation_Pure_Generation.py:277-292),
+    one 256x256 patch.  The chain is chaotic in fp32 itself (1/sqrt(abar_999) = 8970 on the first step), so
+    parity is teacher-forced: every one of the 50 model calls is compared with the fp32 oracle on OUR state (rel-L2 <=
+    5e-3, max-abs <= 2e-2 max|ref|, with |x_t| reaching ~1e5 early on) and every scheduler update must be bit-exact."""
+    from s1s2_b200 import schedule
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    x, cond = _inputs(1, 256, 256, seed=502)
+    worst = _teacher_forced(env, schedule.steps_eps_grid_a(env["abar"], 999, 50), cond, x)
+    print(f"[config 2 parity] 50 teacher-forced model calls at 256x256: worst per-step eps rel-L2 {worst:.2e}")
+
+
 def test_v_ddim_grid_b_teacher_forced(env):
     from s1s2_b200 import schedule
     x, cond = _inputs(2, 32, 32, seed=22)
