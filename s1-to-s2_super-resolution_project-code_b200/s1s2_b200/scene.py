@@ -11,7 +11,7 @@ world size: the initial noise of a patch is keyed by its global index and every 
 import numpy as np
 import torch
 
-from . import patch, samplers, schedule
+from . import patch, samplers
 
 
 def patch_noise(indices, shape, seed_base, device):

@@ -2,7 +2,6 @@
 usage: python tools/diag.py layers B H W | time B steps"""
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "s1-to-s2_super-resolution_project-code_b200"), os.path.join(ROOT, "tests")):
@@ -58,7 +57,6 @@ def main():
 
 def loop_mode():
     """python tools/diag.py loop B layer_idx[,layer_idx..] reps : each layer alone, perf modes 0..3, with clocks."""
-    import subprocess
     sys.path.insert(0, ROOT)
     import bench
     B, reps = int(sys.argv[2]), int(sys.argv[4])
