@@ -1,27 +1,36 @@
 #!/usr/bin/env python
-"""DDIM-50 patches/sec of the S1->S2 sampling path on N B200s (one process per GPU), next to the CPU oracle.
+"""DDIM-50 patches/sec of the S1->S2 sampling path on N B200s (one process per GPU), next to the reference's CPU path and
+the library path (PyTorch eager + cuDNN) it would take on the same GPU.
 
-A "step" is one complete DDIM-50 sampling (50 fused model calls + scheduler updates) of one batch of synthetic
-256x256 patches per GPU.  Workloads (BASELINE.json configs):
-  v64   v-prediction UNet, grid B (0..999, 50 entries), eta=0, batch 64 per GPU     [default; north-star target]
-  eps16 eps-prediction UNet, grid A (999 -> 0, 50 calls), batch 16 per GPU
-  sweep v-prediction UNet, grid B with 10 / 25 / 50 / 100 / 250 steps (BASELINE config 4, DDIM_Sweep): one JSON line with a
-        `sweep` table of ms per model call and patches/s per step count (`value` = the 50-step row)
-  scene one 4x2048x2048 scene tiled by Patch.py's rule, patch-sharded over the ranks, gathered and stitched (config 5)
+A "step" is one complete DDIM-50 sampling (50 fused model calls + scheduler updates) of one batch of synthetic 256x256
+patches per GPU.  Workloads (BASELINE.json configs):
+  v64     v-prediction UNet, grid B (0..999, 50 entries), eta=0, batch 64 per GPU     [default; north-star target]
+  eps16   eps-prediction UNet, grid A (999 -> 0, 50 calls), batch 16 per GPU
+  sweep   v-prediction UNet, grid B with 10 / 25 / 50 / 100 / 250 steps (config 4, DDIM_Sweep): one JSON line with a `sweep`
+          table of ms per model call and patches/s per step count (`value` = the 50-step row)
+  scene   one 4x2048x2048 scene tiled by Patch.py's rule, patch-sharded over the ranks, gathered and stitched (config 5)
+  latency the reference scripts' own operating point: batch 1 (and 2 / 4 / 8 / 16), DDIM-50, through (i) the fused
+          s1s2_sample loop and (ii) the 2-line drop-in of INTEGRATION.md (UNetSmallB200.forward + the script's own
+          torch scheduler), next to PyTorch eager + cuDNN at batch 1
 Patches are independent units: N GPUs = N x batch patches per step, no data-path collective ("weak" scaling).
 
-  value     patches/s with inputs resident in HBM (CUDA events, barrier + synchronize on both sides, max over ranks)
-  e2e       the same through the host-buffer entry s1s2_sample_host (pinned host cond + noise in, image out)
-  roofline  tensor-pipe roofline of the conv kernel family (every launch in the timed region is one instantiation of
-            conv kernel family): algorithmic FLOPs (301 851 475 968 per patch per model call)
-            / device time, against MEASURED_PEAKS.json's sustained bf16 figure; `layers` lists every launch of one
-            model call timed with a CUDA event pair on the launching stream.
-  cpu_baseline  oracle/ (a port of the reference's PyTorch sampler) timed on this box's host cores, bounded sample.
+The default line carries, besides the contract keys:
+  e2e       the same metric through the host-buffer entry s1s2_sample_host_stream (pinned host cond + noise in, image out)
+  roofline  tensor-pipe roofline of the conv kernel family (every launch in the timed region is one instantiation of it):
+            algorithmic FLOPs (301 851 475 968 per patch per model call) / device time, against
+            MEASURED_PEAKS.json's sustained bf16 figure; `layers` = every launch of one model call timed with CUDA event pairs
+  cpu_baseline          oracle/ (a port of the reference's PyTorch sampler) on this box's host cores, one whole chain
+  gpu_library_baseline  the same oracle module on `cuda` = PyTorch eager + cuDNN, the path the unmodified reference takes on
+                        this GPU: TF32 batch 1 (the scripts as written) and fp16 autocast + channels_last batch 64 (best case)
+  latency   the batch 1..16 table of the `latency` workload (rank 0, N = 1)
+  scene     config 5 at this N: one 2048^2 scene at stride 64 and at Patch.py's default stride 32, with per-phase times
+            and the sha256 of the stitched canvas (must not depend on N)
 
-`--impl reference` times only the CPU oracle port (the reference is Python/PyTorch and does not travel to the GPU
-box; oracle/ is its restatement, pinned against vectors the real reference produced: tests/golden/).
+`--impl reference` times only the CPU oracle port (the reference is Python/PyTorch and does not travel to the GPU box;
+oracle/ is its restatement, pinned against vectors the real reference produced: tests/golden/).
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -38,6 +47,7 @@ for _p in (ROOT, PKG):
 FLOP_PER_CALL = 301_851_475_968          # per 256x256 patch per model call (measured on the reference)
 H = W = 256
 N_CALLS = 50
+SEED_V, SEED_EPS = 1235, 1234            # synthetic stand-ins for Models/ddpm_s1_to_s2_upgraded_v.pth / _v3.pth
 
 
 def layer_flops():
@@ -65,6 +75,17 @@ def peaks():
         d = json.load(open(p))
         return float(d["bf16_tflops_sustained"]), float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def csrc_fingerprint():
+    """sha256 (16 hex) over the kernel sources: an ncu capture is only quoted while the kernels it profiled are unchanged."""
+    h = hashlib.sha256()
+    d = os.path.join(PKG, "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def synthetic_batch(B, seed):
@@ -123,20 +144,29 @@ class ClockSampler:
 def make_steps(workload, abar):
     from s1s2_b200 import schedule
     import torch
-    if workload == "v64":
-        steps = schedule.steps_grid_b(abar, schedule.grid_b(999, 50), "v")
-        return steps, float(torch.sqrt(1 - abar[999]))
-    steps = schedule.steps_eps_grid_a(abar, 999, 50)
-    return steps, 1.0
+    if workload == "eps16":
+        return schedule.steps_eps_grid_a(abar, 999, 50), 1.0
+    steps = schedule.steps_grid_b(abar, schedule.grid_b(999, 50), "v")
+    return steps, float(torch.sqrt(1 - abar[999]))
 
 
+def build_model(seed, max_batch, dev):
+    """UNetSmallB200 with the synthetic checkpoint of `seed` loaded the way the reference scripts load theirs."""
+    import s1s2_b200
+    sd = s1s2_b200.synthetic_checkpoint(seed)
+    model = s1s2_b200.UNetSmallB200(8, 4, 96, max_batch=max_batch).to(dev)
+    model.load_state_dict({k: v.to(dev) for k, v in sd.items()}, strict=True)
+    return model.eval()
+
+
+# ====================================================================================== baselines (measurement only)
 def cpu_oracle_sample(workload, n_calls, threads):
     """Times `n_calls` model calls + scheduler updates of the DDIM-50 chain of ONE patch in the CPU oracle; returns
-    (seconds, patches/s extrapolated to the 50-call chain)."""
+    seconds.  (bench.py's cpu_baseline / reference-arm leg: the one place outside tests/ that executes oracle/.)"""
     import torch
     from oracle import samplers as osamplers, schedule as osched, unet as ounet
     torch.set_num_threads(threads)
-    sd = ounet.init_state_dict(8, 4, 96, seed=1234 if workload == "eps16" else 1235)
+    sd = ounet.init_state_dict(8, 4, 96, seed=SEED_EPS if workload == "eps16" else SEED_V)
     model = ounet.OracleModel(sd)
     _, _, abar = osched.make_schedule(1000)
     cond, noise = synthetic_batch(1, 2024)
@@ -153,17 +183,94 @@ def cpu_oracle_sample(workload, n_calls, threads):
     counted.outc = model.outc
     t0 = time.perf_counter()
     try:
-        if workload == "v64":
-            osamplers.ddim_v_grid_b(counted, cond, abar, noise, 50)
-        else:
+        if workload == "eps16":
             osamplers.ddim_eps_grid_a(counted, cond, abar, noise, 999, 50)
+        else:
+            osamplers.ddim_v_grid_b(counted, cond, abar, noise, 50)
     except Stop:
         pass
-    dt = time.perf_counter() - t0
-    return dt, 1.0 / (dt * N_CALLS / calls["n"])
+    return time.perf_counter() - t0
+
+
+def gpu_library_baseline(dev, budget_s=12.0):
+    """The path the UNMODIFIED reference takes on this GPU: eager PyTorch dispatching to cuDNN.
+    The reference tree does not travel to the GPU box, so this runs oracle/'s restatement of the same module and v-DDIM loop
+    (pinned against the reference's outputs) on `cuda`.  Measurement only -- nothing here is on the product path.
+      tf32_b1      fp32 tensors, cudnn.allow_tf32 = True (PyTorch default), batch 1: the batch-1 scripts as written
+      fp16_cl_b64  torch.autocast(float16) (Limitation_Test_v_Prediction.py:205-207) + channels_last, batch 64: the best
+                   cuDNN configuration found (tools/cudnn_baseline.py tries the others)"""
+    import torch
+    from oracle import samplers as osamplers, schedule as osched, unet as ounet
+    sd = ounet.init_state_dict(8, 4, 96, seed=SEED_V)
+    _, _, abar = osched.make_schedule(1000)
+    abar_d = abar.to(dev)
+    rows = []
+    t_begin = time.perf_counter()
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        for mode, B, n_calls in (("tf32", 1, 50), ("fp16_cl", 64, 50)):
+            if time.perf_counter() - t_begin > budget_s:
+                rows.append({"mode": mode, "batch": B, "skipped": "time budget"})
+                continue
+            torch.backends.cudnn.allow_tf32 = True
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.benchmark = True
+            cond, noise = synthetic_batch(B, 2024)
+            cond, noise = cond.to(dev), noise.to(dev)
+            sdd = {k: v.to(dev) for k, v in sd.items()}
+            if mode == "fp16_cl":
+                sdd = {k: (v.contiguous(memory_format=torch.channels_last) if v.ndim == 4 else v) for k, v in sdd.items()}
+                cond = cond.contiguous(memory_format=torch.channels_last)
+                noise = noise.contiguous(memory_format=torch.channels_last)
+            base = ounet.OracleModel(sdd)
+            calls = {"n": 0, "limit": 2}
+
+            class Stop(Exception):
+                pass
+
+            def model(x, t, base=base, calls=calls, mode=mode):
+                if calls["n"] >= calls["limit"]:
+                    raise Stop()
+                calls["n"] += 1
+                if mode == "fp16_cl":
+                    with torch.autocast("cuda", dtype=torch.float16):
+                        return base(x, t.to(x.device)).float()
+                return base(x, t.to(x.device))
+            model.outc = base.outc
+
+            def chain(limit):
+                calls["n"], calls["limit"] = 0, limit
+                try:
+                    osamplers.ddim_v_grid_b(model, cond, abar_d, noise, 50)
+                except Stop:
+                    pass
+            try:
+                chain(3)                                       # cuDNN autotune + warm-up
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                chain(n_calls)
+                e1.record()
+                torch.cuda.synchronize()
+                ms_call = e0.elapsed_time(e1) / calls["n"]
+                rows.append({"mode": mode, "batch": B, "model_calls_timed": calls["n"], "ms_per_model_call": round(ms_call, 3),
+                             "patches_per_s": round(B / (ms_call * N_CALLS / 1e3), 3),
+                             "tflops": round(FLOP_PER_CALL * B / (ms_call / 1e3) / 1e12, 1)})
+            except RuntimeError as e:                          # e.g. out of memory next to the product arena
+                rows.append({"mode": mode, "batch": B, "error": str(e)[:160]})
+            del base, sdd, cond, noise
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return {"what": f"oracle/ restatement of the reference's UNetSmall + v-DDIM loop on cuda: PyTorch {torch.__version__} "
+                    f"eager + cuDNN {torch.backends.cudnn.version()} (the library path of the unmodified reference); DDIM-50 patches/s",
+            "rows": rows, "wall_s": round(time.perf_counter() - t_begin, 1)}
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU implementation of the path (oracle/ port), all host threads.  Each step is a
+    bounded sample -- the first `n_calls` of the 50 model calls (+ scheduler updates) of one patch's chain; `ms_per_step` is
+    what was really timed per step and `value` is the DDIM-50 patches/s that per-call time implies."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
@@ -175,79 +282,177 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         cpu_oracle_sample(args.workload, n_calls, threads)
     dt = time.perf_counter() - t0
-    pps = args.steps / (dt * N_CALLS / n_calls)
-    sample = (f"each step = {n_calls} of the 50 model calls (+ scheduler updates) of one 256x256 patch, oracle/ fp32 "
-              f"PyTorch CPU, {threads} threads; patches/s extrapolated x{N_CALLS // n_calls}")
+    s_per_call = dt / (args.steps * n_calls)
+    pps = 1.0 / (s_per_call * N_CALLS)
+    sample = (f"each step = the first {n_calls} of the 50 model calls (+ scheduler updates) of one 256x256 patch's chain, "
+              f"oracle/ fp32 PyTorch CPU, {threads} threads; ms_per_step is the time of that sample; value = 1 / (50 x the "
+              f"measured time per model call) -- a whole chain measured the same way agrees within 4 % (cpu_baseline of the main arm)")
+    cfg = config_block(args, world)
+    cfg["arithmetic"] = "f32 (PyTorch CPU: oneDNN convolutions, ATen elementwise)"
     line = {"impl": "reference", "metric": "DDIM-50 patches/sec", "value": pps, "unit": "patches/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * N_CALLS / n_calls,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_block(args, world),
+            "config": cfg, "sample_model_calls_per_step": n_calls, "model_calls_per_patch": N_CALLS,
             "cpu_baseline": {"value": pps, "unit": "patches/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": pps, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_scene(args, rank, world, dev):
-    """BASELINE config 5: one synthetic 4 x 2048 x 2048 Sentinel-1 scene, Patch.py tiling (256 / stride 64 = 841 patches)
-    sharded patch-wise over the ranks, v-DDIM-50, NCCL gather, overlap-blend stitch on rank 0.  Strong scaling: a step
-    is the whole scene; value = patches / max-over-ranks device time."""
+# ====================================================================================== blocks of the default line
+def script_style_v_ddim(model, cond, abar_d, noise, idxs):
+    """The reference script's own sampling loop with only the model swapped ("2-line change"): what
+    DDIM_Multi-step_v_Prediction.py:153-175 executes per step -- torch.cat, one model call, the v -> (x0, eps) conversion and
+    the DDIM update as eager torch elementwise ops -- here around UNetSmallB200.forward (s1s2_forward)."""
+    import torch
+    B = cond.shape[0]
+    K = int(idxs[-1])
+    x = noise * torch.sqrt(1 - abar_d[K])
+    for i in reversed(range(len(idxs))):
+        t = int(idxs[i])
+        t_idx = torch.full((B,), t, dtype=torch.long, device=cond.device)
+        a_t = abar_d[t]
+        v = model(torch.cat([x, cond], dim=1), t_idx)
+        sa, sb = torch.sqrt(a_t), torch.sqrt(1 - a_t)
+        x0 = sa * x - sb * v
+        eps = sb * x + sa * v
+        if i == 0:
+            x = x0
+            break
+        a_prev = abar_d[int(idxs[i - 1])]
+        x = torch.sqrt(a_prev) * x0 + torch.sqrt(1 - a_prev) * eps
+    return torch.clamp(x, 0.0, 1.0)
+
+
+def latency_table(model, abar, dev, batches=(1, 2, 4, 8, 16), target_s=0.4):
+    """DDIM-50 at small batches (the reference scripts run batch 1): per batch the fused loop (s1s2_sample: one library call
+    enqueues 50 model calls) and the script-style drop-in loop; device time by CUDA events over whole chains, plus the host
+    time spent enqueueing (when it exceeds the device time the path is launch-bound)."""
+    import torch
+    from s1s2_b200 import samplers, schedule
+    peak_tf, _, _ = peaks()
+    idxs = schedule.grid_b(999, 50)
+    steps = schedule.steps_grid_b(abar, idxs, "v")
+    init_scale = float(torch.sqrt(1 - abar[999]))
+    abar_d = abar.to(dev)
+    rows = []
+    for B in batches:
+        cond_h, noise_h = synthetic_batch(B, 4000 + B)
+        cond, noise = cond_h.to(dev), noise_h.to(dev)
+        row = {"batch": B}
+        for name, fn in (("fused", lambda: samplers.run_steps(model, steps, cond, noise, init_scale=init_scale)),
+                         ("dropin", lambda: script_style_v_ddim(model, cond, abar_d, noise, idxs))):
+            for _ in range(2):
+                out = fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            out = fn()
+            e1.record()
+            host_one = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            one = e0.elapsed_time(e1) / 1e3
+            reps = max(2, min(40, int(target_s / max(one, 1e-4))))
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(reps):
+                out = fn()
+            e1.record()
+            host = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            ms_chain = e0.elapsed_time(e1) / reps
+            assert bool(torch.isfinite(out).all())
+            tf = FLOP_PER_CALL * N_CALLS * B / (ms_chain / 1e3) / 1e12
+            row[name] = {"chains_timed": reps, "ms_per_chain": round(ms_chain, 3), "ms_per_model_call": round(ms_chain / N_CALLS, 4),
+                         "patches_per_s": round(B / (ms_chain / 1e3), 2), "tflops": round(tf, 1), "frac_of_peak": round(tf / peak_tf, 4),
+                         "host_enqueue_ms_per_chain": round(host / reps * 1e3, 3), "first_chain_host_ms": round(host_one * 1e3, 3)}
+        if B == 1:
+            res_f = samplers.run_steps(model, steps, cond, noise, init_scale=init_scale)
+            res_d = script_style_v_ddim(model, cond, abar_d, noise, idxs)
+            row["fused_vs_dropin_max_abs_diff"] = float((res_f - res_d).abs().max())
+        rows.append(row)
+    return rows
+
+
+def scene_block(model, abar, dev, rank, world, batch):
+    """BASELINE config 5 at this world size: one synthetic 4 x 2048 x 2048 Sentinel-1 scene held in pinned HOST memory, uploaded,
+    tiled by Patch.py's rule (256 / stride 64 = 841 windows, and Patch.py's default stride 32 = 3249), patch-sharded over the
+    ranks, v-DDIM-50, NCCL gather to rank 0, overlap-blend stitch, canvas downloaded.  Strong scaling: the whole scene is the
+    unit.  canvas_sha256 must be the same for every world size (pure sharding, noise keyed by global patch index)."""
     import torch
     import torch.distributed as dist
-    import s1s2_b200
-    from s1s2_b200 import scene as sc, schedule
-    from oracle import unet as ounet
-    sd = ounet.init_state_dict(8, 4, 96, seed=1235)
-    model = s1s2_b200.UNetSmallB200(8, 4, 96, max_batch=args.batch).to(dev)
-    model.load_state_dict(sd, strict=True)
-    model.eval()
-    _, _, abar = schedule.derive(schedule.cosine_beta_schedule(1000))
-    scn = sc.synthetic_scene(2048, 2048, seed=0).to(dev)
-    model.engine(dev, 256, 256, args.batch)
-
-    def once():
-        return sc.generate_scene(model, scn, abar, ps=256, stride=64, param="v", steps=50, t_start=999, batch=args.batch,
-                                 rank=rank, world=world)
-
-    def sync():
+    from s1s2_b200 import scene as sc
+    scn = sc.synthetic_scene(2048, 2048, seed=0).pin_memory()
+    out = []
+    for stride in (64, 32):
+        tm = {}
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
-    for _ in range(max(1, args.warmup // 3)):
-        res = once()
-    sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res, up, down = sc.generate_scene_host(model, scn, abar, dev, rank=rank, world=world, ps=256, stride=stride, param="v",
+                                               steps=50, t_start=999, batch=batch, timings=tm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        keys = ("extract_ms", "noise_ms", "sample_ms", "gather_ms", "stitch_ms")
+        vec = torch.tensor([ms] + [tm.get(k, 0.0) for k in keys], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+        vec = vec.tolist()
+        if rank == 0:
+            n = int(res["kept"].sum())
+            sha = hashlib.sha256(res["canvas"].numpy().tobytes()).hexdigest()
+            row = {"stride": stride, "patches": n, "ms_total": round(vec[0], 2), "patches_per_s": round(n / (vec[0] / 1e3), 2)}
+            row.update({k: round(v, 3) for k, v in zip(keys, vec[1:])})
+            row.update({"h2d_bytes": up, "d2h_bytes": down, "canvas_sha256": sha,
+                        "covered_fraction": round(float(res["cover"].float().mean()), 6)})
+            out.append(row)
+        del res
+        torch.cuda.empty_cache()
+    return {"what": "Evaluation_Pure_Generation over a whole scene (config 5): 4x2048x2048 synthetic Sentinel-1 scene in pinned host "
+                    "memory -> upload -> Patch.py tiling -> patch-sharded v-DDIM-50 -> NCCL gather -> overlap-blend stitch -> download; "
+                    "phase times = max over ranks (CUDA events)", "n_gpus": world, "batch_per_gpu": batch, "rows": out} if rank == 0 else None
+
+
+# ====================================================================================== stand-alone workloads
+def run_scene(args, rank, world, dev):
+    import torch
+    import torch.distributed as dist
+    from s1s2_b200 import schedule
+    model = build_model(SEED_V, args.batch, dev)
+    _, _, abar = schedule.derive(schedule.cosine_beta_schedule(1000))
+    model.engine(dev, 256, 256, args.batch)
+    steps, init_scale = make_steps("v64", abar)
+    from s1s2_b200 import samplers
+    cond_h, noise_h = synthetic_batch(args.batch, 2024 + rank)
+    for _ in range(max(1, args.warmup // 3)):                         # clocks and caches warm before the scene is timed
+        samplers.run_steps(model, steps, cond_h.to(dev), noise_h.to(dev), init_scale=init_scale)
+    torch.cuda.synchronize()
     clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     l0 = model.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        res = once()
-    e1.record()
-    sync()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    blk = scene_block(model, abar, dev, rank, world, args.batch)
     clk = clocks.stop()
     if rank == 0:
-        n = int(res["kept"].sum())
-        value = n * args.steps / (ms / 1e3)
+        r64 = blk["rows"][0]
         peak_tf, _, peak_src = peaks()
-        achieved = value * N_CALLS * FLOP_PER_CALL / 1e12 / world
-        line = {"metric": "DDIM-50 patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        achieved = r64["patches"] / (r64["sample_ms"] / 1e3) * N_CALLS * FLOP_PER_CALL / 1e12 / world
+        line = {"metric": "DDIM-50 patches/sec", "value": r64["patches_per_s"], "unit": "patches/s", "n_gpus": world, "steps": 1,
+                "warmup": args.warmup, "ms_per_step": r64["ms_total"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": "Evaluation_Pure_Generation over a whole scene: 4x2048x2048 synthetic Sentinel-1 scene, Patch.py "
                            "tiling 256/stride 64 (841 patches), v-DDIM-50, patch-sharded, NCCL gather to rank 0, overlap-blend stitch",
-                           "batch_per_gpu": args.batch, "patches": n, "parallelism": f"patch-sharded x{world}, one gather",
+                           "batch_per_gpu": args.batch, "patches": r64["patches"], "parallelism": f"patch-sharded x{world}, one gather",
                            "l2": "working set exceeds L2"},
-                "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                        "entry": "s1s2_b200.scene.generate_scene (scene resident on the device; tile extract -> sample -> gather -> stitch)"},
-                "gpu_launches": int(model.launch_count() - l0), "clocks": clk,
+                "e2e": {"value": r64["patches_per_s"], "unit": "patches/s", "h2d_bytes_per_step": r64["h2d_bytes"],
+                        "d2h_bytes_per_step": r64["d2h_bytes"],
+                        "entry": "s1s2_b200.scene.generate_scene_host (pinned host scene in, host canvas out)"},
+                "gpu_launches": int(model.launch_count() - l0), "clocks": clk, "scene": blk,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                              "peak_source": peak_src, "traffic": None,
-                             "kernel": "conv kernel family, per GPU, over the whole scene step (extract/stitch/gather included in time)"},
+                             "kernel": "conv kernel family, per GPU, over the sampling phase of the stride-64 scene (slowest rank)"},
                 "cpu_baseline": None}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -260,13 +465,9 @@ def run_sweep(args, rank, world, dev):
     each, t = 0 included), batch 64 per GPU; per-call latency and patches/s per step count."""
     import torch
     import torch.distributed as dist
-    import s1s2_b200
     from s1s2_b200 import samplers, schedule
-    from oracle import unet as ounet
     B = args.batch
-    model = s1s2_b200.UNetSmallB200(8, 4, 96, max_batch=B).to(dev)
-    model.load_state_dict(ounet.init_state_dict(8, 4, 96, seed=1235), strict=True)
-    model.eval()
+    model = build_model(SEED_V, B, dev)
     _, _, abar = schedule.derive(schedule.cosine_beta_schedule(1000))
     cond_h, noise_h = synthetic_batch(B, 2024 + rank)
     cond_d, noise_d = cond_h.to(dev), noise_h.to(dev)
@@ -321,11 +522,46 @@ def run_sweep(args, rank, world, dev):
         dist.destroy_process_group()
 
 
+def run_latency(args, rank, world, dev):
+    """The reference scripts' operating point (batch 1) as its own line: `value` = fused DDIM-50 patches/s at batch 1."""
+    import torch
+    from s1s2_b200 import schedule
+    if rank != 0:
+        return
+    model = build_model(SEED_V, 16, dev)
+    _, _, abar = schedule.derive(schedule.cosine_beta_schedule(1000))
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    l0 = model.launch_count()
+    rows = latency_table(model, abar, dev)
+    clk = clocks.stop()
+    lib = None if args.no_library_baseline else gpu_library_baseline(dev)
+    peak_tf, _, peak_src = peaks()
+    b1 = rows[0]["fused"]
+    layers = None
+    if not args.no_layers:
+        fl = dict(layer_flops())
+        layers = {}
+        for B in (1, 4):
+            lt = model.profile_layers(dev, H, W, B, reps=20)
+            layers[f"b{B}"] = [{"layer": n, "ms": round(t, 4), "tflops": round(fl[n] * B / (t / 1e3) / 1e12, 1)} for n, t in lt]
+    line = {"metric": "DDIM-50 patches/sec", "value": b1["patches_per_s"], "unit": "patches/s", "n_gpus": 1, "steps": b1["chains_timed"],
+            "warmup": 2, "ms_per_step": b1["ms_per_chain"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "latency: DDIM_Multi-step_v_Prediction at the scripts' own batch 1 (and 2/4/8/16), v-DDIM-50, one "
+                                   "256x256 patch per chain; fused s1s2_sample loop and the INTEGRATION.md 2-line drop-in loop",
+                       "batch_per_gpu": 1, "ddim_steps": 50, "l2": "at batch 1 the 123 MB activation arena is L2-sized: warm-cache "
+                       "numbers, as in the reference's own back-to-back steps"},
+            "latency": rows, "gpu_library_baseline": lib, "layers": layers, "gpu_launches": int(model.launch_count() - l0), "clocks": clk,
+            "roofline": {"bound": "tensor", "achieved": b1["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": b1["tflops"] / peak_tf,
+                         "peak_source": peak_src, "traffic": None}, "e2e": None, "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+
+
 def config_block(args, world):
     B = args.batch
-    return {"workload": ("DDIM_Multi-step_v_Prediction: v-prediction UNetSmall(8,4,96), grid B 0..999 (50 calls), eta=0"
-                         if args.workload == "v64" else
-                         "DDIM_Multi-step / Evaluation_Pure_Generation: eps-prediction UNetSmall(8,4,96), grid A 999->0 (50 calls)"),
+    return {"workload": ("DDIM_Multi-step / Evaluation_Pure_Generation: eps-prediction UNetSmall(8,4,96), grid A 999->0 (50 calls)"
+                         if args.workload == "eps16" else
+                         "DDIM_Multi-step_v_Prediction: v-prediction UNetSmall(8,4,96), grid B 0..999 (50 calls), eta=0"),
             "patch": "4x256x256 cond + 4x256x256 noise (Patch.py shape)", "batch_per_gpu": B, "global_batch": B * world,
             "ddim_steps": 50, "weights": "random init (Models/*.pth absent from the reference tree)",
             "arithmetic": "f16 operands, f32 accumulate (TMEM), f32 bias / epilogue / scheduler state (x_t carried as an f16 hi/lo pair)",
@@ -339,11 +575,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="v64", choices=["v64", "eps16", "scene", "sweep"])
+    ap.add_argument("--workload", default="v64", choices=["v64", "eps16", "scene", "sweep", "latency"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layers", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--no-scene", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="main arm only (no cpu / library baselines, latency table, scene block)")
     args = ap.parse_args()
+    if args.quick:
+        args.no_cpu_baseline = args.no_latency = args.no_library_baseline = args.no_scene = True
     if args.batch is None:
         args.batch = 16 if args.workload == "eps16" else 64
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -374,9 +616,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
 
-    import s1s2_b200
     from s1s2_b200 import samplers, schedule
-    from oracle import unet as ounet               # weights only: the synthetic checkpoint both sides load
 
     if args.workload == "scene":
         run_scene(args, rank, world, dev)
@@ -384,12 +624,15 @@ def main():
     if args.workload == "sweep":
         run_sweep(args, rank, world, dev)
         return
+    if args.workload == "latency":
+        run_latency(args, rank, world, dev)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     B = args.batch
-    sd = ounet.init_state_dict(8, 4, 96, seed=1234 if args.workload == "eps16" else 1235)
-    model = s1s2_b200.UNetSmallB200(8, 4, 96, max_batch=B).to(dev)
-    model.load_state_dict(sd, strict=True)
-    model.eval()
+    model = build_model(SEED_EPS if args.workload == "eps16" else SEED_V, B, dev)
     _, _, abar = schedule.derive(schedule.cosine_beta_schedule(1000))
     steps, init_scale = make_steps(args.workload, abar)
     assert len(steps) == N_CALLS
@@ -429,19 +672,27 @@ def main():
     patches = B * world * args.steps
     value = patches / (ms / 1e3)
 
-    # ---------------------------------------------------------------- end-to-end arm (host buffers)
-    samplers.run_steps_host(model, steps, cond_h, noise_h, init_scale=init_scale, device=dev)
+    # ---------------------------------------------------------------- end-to-end arm (host buffers, pipelined entry)
+    # one library call per timed region: all `steps` batches go through s1s2_sample_host_stream, which uploads batch i+1 and
+    # downloads batch i-1 under the model calls of batch i; every byte in and out is a real pinned-host <-> device copy.
+    n_e2e = B * args.steps
+    cond_all = cond_h.repeat(args.steps, 1, 1, 1).pin_memory()
+    noise_all = noise_h.repeat(args.steps, 1, 1, 1).pin_memory()
+    samplers.run_steps_host(model, steps, cond_h, noise_h, init_scale=init_scale, device=dev, batch=B)
+    samplers.host_result_buffer(model, noise_all.shape)          # pinned result buffer exists before the clock starts
     sync()
     e0.record()
-    for _ in range(args.steps):
-        res = samplers.run_steps_host(model, steps, cond_h, noise_h, init_scale=init_scale, device=dev)
+    res = samplers.run_steps_host(model, steps, cond_all, noise_all, init_scale=init_scale, device=dev, batch=B)
     e1.record()
     sync()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     img_bytes = B * 4 * H * W * 4
     e2e = {"value": patches / (ms_e2e / 1e3), "unit": "patches/s", "h2d_bytes_per_step": 2 * img_bytes * world,
-           "d2h_bytes_per_step": img_bytes * world, "entry": "s1s2_sample_host (pinned host cond + noise -> host image)"}
-    assert bool(torch.equal(res, out.cpu())), "host-buffer entry disagrees with the device-resident entry"
+           "d2h_bytes_per_step": img_bytes * world,
+           "entry": "s1s2_sample_host_stream (pinned host cond + noise -> host image; copies of neighbouring batches overlap the model calls)"}
+    assert res.shape[0] == n_e2e
+    assert bool(torch.equal(res[-B:], out.cpu())), "host-buffer entry disagrees with the device-resident entry"
+    del cond_all, noise_all
 
     # ---------------------------------------------------------------- roofline of the conv kernel family
     peak_tf, _, peak_src = peaks()
@@ -455,8 +706,14 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp) and B == 64:           # ncu --set full capture of one model call at batch 64 (profiles/)
         tj = json.load(open(tp))
-        roof["traffic"] = tj["dram_total_GB"] * 1e9 / 16                     # DRAM bytes per launch (mean of the 16)
-        roof["traffic_detail"] = {k: tj[k] for k in ("source", "per", "dram_read_GB", "dram_write_GB", "algorithmic_activation_GB")}
+        fp = csrc_fingerprint()
+        if tj.get("csrc_fingerprint") == fp:      # quoted only while the profiled kernels are the ones being timed
+            roof["traffic"] = tj["dram_total_GB"] * 1e9 / 16                     # DRAM bytes per launch (mean of the 16)
+            roof["traffic_detail"] = {k: tj.get(k) for k in ("source", "per", "dram_read_GB", "dram_write_GB",
+                                                             "algorithmic_activation_GB", "git_head", "csrc_fingerprint")}
+        else:
+            roof["traffic_stale"] = (f"profiles/traffic.json was captured for kernel sources {tj.get('csrc_fingerprint')}, "
+                                     f"the tree is at {fp}: re-run tools/gpu_round.sh")
     if not args.no_layers and rank == 0:
         lt = model.profile_layers(dev, H, W, B, reps=3)
         fl = dict(layer_flops())
@@ -464,14 +721,23 @@ def main():
         top = max(roof["layers"], key=lambda r: r["ms"])
         roof["dominant_launch"] = top
 
+    lat = lib = None
+    if rank == 0 and world == 1:
+        if not args.no_latency:
+            lat = latency_table(model, abar, dev)
+        if not args.no_library_baseline:
+            lib = gpu_library_baseline(dev)
+    scene = None
+    if not args.no_scene and args.workload == "v64":
+        scene = scene_block(model, abar, dev, rank, world, B)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cpu_oracle_sample(args.workload, 1, threads)
-        n_calls = N_CALLS
-        dt, pps = cpu_oracle_sample(args.workload, n_calls, threads)
-        cpu = {"value": pps, "unit": "patches/s", "cores": threads, "kind": "port",
-               "sample": f"one complete DDIM-50 chain (all {n_calls} model calls + scheduler updates) of one 256x256 patch "
+        dt = cpu_oracle_sample(args.workload, N_CALLS, threads)
+        cpu = {"value": 1.0 / dt, "unit": "patches/s", "cores": threads, "kind": "port",
+               "sample": f"one complete DDIM-50 chain (all {N_CALLS} model calls + scheduler updates) of one 256x256 patch "
                          f"({dt:.1f} s), oracle/ fp32 PyTorch CPU, {threads} threads"}
 
     if rank == 0:
@@ -479,7 +745,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic", "config": config_block(args, world), "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "gpu_library_baseline": lib, "latency": lat, "scene": scene}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

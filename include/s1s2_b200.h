@@ -75,7 +75,9 @@ int s1s2_load_weights(s1s2_handle* h, int n, const char* const* names, const flo
                       const int64_t* numel, void* stream);
 
 /* Replaces `model(torch.cat([x_t, x_cond], dim=1), t_idx)` (Evaluation/DDIM_Multi-step.py:43-53,131).
- * xt_and_cond: f32[B,8,H,W]; t_idx: int64[B]; out: f32[B,4,H,W] (all device). */
+ * xt_and_cond: f32[B,8,H,W]; t_idx: int64[B]; out: f32[B,4,H,W] (all device).  Timesteps must lie in [0, 2048] (the
+ * fp16-exact integer range of the time planes; the reference uses T = 1000): a patch whose t is outside gets NaN output
+ * instead of a silently rounded timestep (t_idx lives on the device, so the check cannot be a host error code). */
 int s1s2_forward(s1s2_handle* h, const float* xt_and_cond, const int64_t* t_idx, float* out, int B, void* stream);
 
 /* Replaces the whole sampling loop of ddpm_ddim_generate / ddim_multistep_eval[_v] / ddim_sample / sample_ddim_v /
@@ -102,11 +104,28 @@ int s1s2_set_noise_seed(s1s2_handle* h, uint64_t seed, uint32_t patch_base);
 int s1s2_sample_host(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond_host,
                      const float* x_init_host, float init_scale, float* out_host, int B, void* stream);
 
+/* The same for N >= 1 patches held in host memory, processed in batches of `batch` (<= max_batch) through a three-stream
+ * pipeline: the upload of batch i+1 and the download of batch i-1 run under the model calls of batch i (two staging sets on
+ * the device).  This is the per-file loop of the reference drivers (DDIM_Multi-step.py:219-246: load .npz -> .to(device) ->
+ * sample -> .cpu()) for a whole list of files.  cond_host / x_init_host / out_host: f32[N,4,H,W]; pinned memory recommended
+ * (pageable memory serialises the copies).  Synchronises `stream` and its two internal copy streams before returning. */
+int s1s2_sample_host_stream(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond_host,
+                            const float* x_init_host, float init_scale, float* out_host, int N, int batch, void* stream);
+
+/* Unit-normal initial noise for N patches keyed by GLOBAL patch id: Philox4x32-10, key = seed, counter = (element / 4,
+ * patch id, tag), Box-Muller.  A patch draws the same noise on whichever rank / batch slot it lands, so a sharded scene
+ * equals the single-GPU scene bit for bit.  (The reference seeds torch's generator per file, DDIM_Sweep.py:193,404; the
+ * drivers keep doing that -- this entry serves the whole-scene path, which has no reference counterpart.)
+ *   patch_ids int64[N] device; out f32[N, elems_per_patch] device, 16-byte aligned; elems_per_patch % 4 == 0; N <= 65535 */
+int s1s2_patch_noise(int device, uint64_t seed, const int64_t* patch_ids, int N, int64_t elems_per_patch, float* out,
+                     void* stream);
+
 /* Tile extraction + per-patch normalisation (Patch.py:80-84,201-209,226-239) for the windows listed in `origins`.
  *   scene   f32[4,SH,SW] device (HH dB, HV dB, incidence deg, elevation m; may hold NaN/Inf)
  *   vmask   u8[SH,SW] device or NULL: extra validity (Patch.py:41-49's target / collocation terms); a pixel is
  *           valid when all four scene channels are finite and vmask (if given) is non-zero
- *   origins int32[N,2] device (row, col)
+ *   origins int32[N,2] device (row, col); a window that does not lie inside the scene yields an all-invalid patch
+ *           (cond 0, mask 0, valid_ratio 0)
  *   cond    f32[N,4,ps,ps] device out; mask u8[N,ps,ps] device out; valid_ratio f32[N] device out (nullable) */
 int s1s2_tile_extract(int device, const float* scene, const uint8_t* vmask, int SH, int SW, const int32_t* origins,
                       int N, int ps, float* cond, uint8_t* mask, float* valid_ratio, void* stream);
@@ -124,6 +143,11 @@ int s1s2_tile_filter(int device, const float* scene, int Ci, const float* target
 int s1s2_stitch(int device, const float* preds, const int32_t* origins, int N, int C, int ps, int stride, int SH,
                 int SW, float* canvas, uint8_t* cover, void* stream);
 
+/* The same with a separable per-pixel weight window[ly] * window[lx] (f32[ps] device, e.g. a Hann window that is positive
+ * everywhere): canvas = sum(w * pred) / sum(w), accumulated in the same order.  window == NULL is s1s2_stitch. */
+int s1s2_stitch_weighted(int device, const float* preds, const int32_t* origins, int N, int C, int ps, int stride, int SH,
+                         int SW, const float* window, float* canvas, uint8_t* cover, void* stream);
+
 /* Evaluation metrics of N predicted patches in one pass each (the drivers' per-file metric calls:
  * masked_mae / masked_mse / psnr / ssim_simple, Evaluation/DDIM_Multi-step.py:72-101; sam / ergas,
  * Evaluation_Updated/Evaluation_Pure_Generation.py:229-254) plus the per-channel error sums behind the dataset-level
@@ -140,6 +164,13 @@ int s1s2_patch_metrics(int device, const float* pred, const float* gt, const uin
  * packed input record "xin16".  With out_nchw == NULL only the shape (C, H, W) is returned. */
 int s1s2_debug_activation(s1s2_handle* h, const char* name, float* out_nchw, int B, int* C, int* H, int* W,
                           void* stream);
+
+/* Debug aid for the fp16 activation arena ("fp16 overflow"): for every activation view of the LAST
+ * model call (order and names: s1s2_view_name) the number of stored fp16 elements at the saturation value of the conv
+ * epilogues' cvt.rn.satfinite (|v| = 65504) or non-finite -- i.e. how many outputs a layer clamped.  Host-synchronous;
+ * counts is a HOST array [n_out]; with counts == NULL only *n_views is returned. */
+int s1s2_debug_saturation_count(s1s2_handle* h, int B, uint64_t* counts, int n_out, int* n_views, void* stream);
+const char* s1s2_view_name(const s1s2_handle* h, int i);
 
 /* Measurement aid for bench.py's roofline block: runs the denoiser `reps` times at batch B on whatever the arena
  * holds, with a CUDA event pair around every launch on `stream`, and returns the mean duration of each launch in

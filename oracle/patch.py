@@ -138,17 +138,29 @@ def filter_decision(Y, M, valid_ratio_threshold=0.80, variance_threshold=1e-4, d
     return code, (vr, var, dk, lv)
 
 
-def stitch(preds: np.ndarray, origins: np.ndarray, H: int, W: int):
-    """Uniform-weight overlap blend.  preds f32[N,C,ps,ps], origins i32[N,2] -> (canvas f32[C,H,W], cover u8[H,W]).
+def hann_window(ps: int) -> np.ndarray:
+    """w[i] = 0.5 - 0.5 cos(2 pi (i + 0.5) / ps), computed in float64 and rounded to float32 (strictly positive)."""
+    i = np.arange(ps, dtype=np.float64)
+    return (0.5 - 0.5 * np.cos(2.0 * np.pi * (i + 0.5) / ps)).astype(np.float32)
 
-    Accumulates in fp32 in patch-index order and divides once, which is the exact arithmetic the CUDA gather
-    kernel performs per output pixel."""
+
+def stitch(preds: np.ndarray, origins: np.ndarray, H: int, W: int, window: np.ndarray = None):
+    """Overlap blend.  preds f32[N,C,ps,ps], origins i32[N,2] -> (canvas f32[C,H,W], cover u8[H,W]).
+
+    window None: uniform weights.  window f32[ps]: separable weights w[ly] * w[lx].  Accumulates in fp32 in patch-index
+    order and divides once, which is the exact arithmetic the CUDA gather kernel performs per output pixel.
+    PARITY UNPINNED: the reference has no stitch; this states the definition of DESIGN.md."""
     N, C, ps, _ = preds.shape
     acc = np.zeros((C, H, W), np.float32)
     cnt = np.zeros((H, W), np.float32)
+    w2 = None if window is None else (window.astype(np.float32)[:, None] * window.astype(np.float32)[None, :]).astype(np.float32)
     for p in range(N):
         r, c = int(origins[p, 0]), int(origins[p, 1])
-        acc[:, r:r + ps, c:c + ps] += preds[p]
-        cnt[r:r + ps, c:c + ps] += 1.0
-    out = np.where(cnt > 0, acc / np.maximum(cnt, 1.0), 0.0).astype(np.float32)
+        if w2 is None:
+            acc[:, r:r + ps, c:c + ps] += preds[p]
+            cnt[r:r + ps, c:c + ps] += 1.0
+        else:
+            acc[:, r:r + ps, c:c + ps] += (w2[None] * preds[p]).astype(np.float32)
+            cnt[r:r + ps, c:c + ps] += w2
+    out = np.where(cnt > 0, acc / np.where(cnt > 0, cnt, 1.0).astype(np.float32), 0.0).astype(np.float32)
     return out, (cnt > 0).astype(np.uint8)

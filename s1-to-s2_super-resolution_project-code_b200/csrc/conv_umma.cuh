@@ -80,6 +80,7 @@ struct ConvParams {
     CUtensorMap tmap_out2;        // MODE_CONVT: tmap_out / tmap_out2 = output rows 2y / 2y+1 as 5-D (c, kx, x, y, n) views
     const float* bias;            // [num_n_tiles * BLOCK_N]
     const uint32_t* amax_in;      // [B] float bits of max|x_t| per patch for this call (nullptr: scale 1)
+    uint32_t* amax_zero;          // first layer only, nullable: [B] words cleared for this call's head to reduce max|x_next| into
     __half* out;                  // NHWC fp16 destination (channel offset already applied)
     int out_cpitch;               // elements between consecutive destination pixels
     int H, W, B;                  // input image size, live batch
@@ -277,6 +278,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     // launch it overlaps the previous kernel's tail.  Activations, amax and the sampler state are read / written below.
     pdl_launch_dependents();
     pdl_wait();
+    if (warp == 3 && blockIdx.x == 0 && p.amax_zero != nullptr) {       // (warp 3 has no other role)
+        for (int b = lane; b < p.B; b += 32) p.amax_zero[b] = 0u;
+    }
 
     // Both issue loops below run WARP-UNIFORM (all 32 lanes wait on the barriers and keep the loop state; one
     // elected lane issues TMA / MMA / commit).  Uniform control flow lets ptxas keep descriptors and addresses in

@@ -168,6 +168,16 @@ __global__ void __launch_bounds__(kExtractThreads) tile_extract_kernel(const flo
                                                                        float* __restrict__ valid_ratio, int allow_vec) {
     __shared__ double red[32][5];
     const int r0 = origins[2 * blockIdx.x], c0 = origins[2 * blockIdx.x + 1];
+    if (r0 < 0 || c0 < 0 || r0 > SH - ps || c0 > SW - ps) {
+        // a window that does not lie inside the scene (Patch.py's patch_iter never yields one): all-invalid patch
+        const size_t npix = static_cast<size_t>(ps) * ps;
+        float* cp = cond + static_cast<size_t>(blockIdx.x) * 4 * npix;
+        uint8_t* mp = mask + static_cast<size_t>(blockIdx.x) * npix;
+        for (size_t i = threadIdx.x; i < 4 * npix; i += blockDim.x) cp[i] = 0.f;
+        for (size_t i = threadIdx.x; i < npix; i += blockDim.x) mp[i] = 0;
+        if (valid_ratio != nullptr && threadIdx.x == 0) valid_ratio[blockIdx.x] = 0.f;
+        return;
+    }
     if (allow_vec && (c0 & 3) == 0) tile_extract_body<4>(scene, vmask, SH, SW, r0, c0, ps, cond, mask, valid_ratio, red);
     else tile_extract_body<1>(scene, vmask, SH, SW, r0, c0, ps, cond, mask, valid_ratio, red);
 }
@@ -299,6 +309,10 @@ __global__ void __launch_bounds__(kFilterThreads, 4) tile_filter_kernel(const fl
                                                                      FilterThresholds th, float* __restrict__ stats, int allow_vec) {
     __shared__ double red[32][kFilterVals];
     const int r0 = origins[2 * blockIdx.x], c0 = origins[2 * blockIdx.x + 1];
+    if (r0 < 0 || c0 < 0 || r0 > SH - ps || c0 > SW - ps) {           // window outside the scene: fails the valid-ratio test
+        if (threadIdx.x < 8) stats[static_cast<size_t>(blockIdx.x) * 8 + threadIdx.x] = threadIdx.x == 7 ? 1.f : 0.f;
+        return;
+    }
     if (allow_vec && (c0 & 3) == 0) tile_filter_body<4>(scene, Ci, target, colloc, SH, SW, r0, c0, ps, th, stats, red);
     else tile_filter_body<1>(scene, Ci, target, colloc, SH, SW, r0, c0, ps, th, stats, red);
 }
@@ -598,60 +612,103 @@ __global__ void stitch_map_kernel(const int32_t* __restrict__ origins, int N, in
 // One thread per G consecutive canvas pixels of a row (they share their covering patches when stride, ps and x are
 // multiples of G); covering patches visited in ascending (row, col) = ascending patch index, fp32 adds in that order, one
 // fp32 division: no atomics, bit-reproducible, identical for G = 1 and G = 4.
+// win == nullptr: uniform weights (sum / count).  win = f32[ps]: separable window, weight of a patch pixel =
+// win[ly] * win[lx] (e.g. Hann): sum of weight * pred in the same order / sum of weights.
+// blockIdx.y strides over the canvas rows (gridDim.y is capped at 65535).
 template <int G, int CMAX>
 __global__ void __launch_bounds__(128, 8) stitch_gather_kernel(const float* __restrict__ preds,
                                                             const int32_t* __restrict__ grid_map, int C, int ps, int stride,
                                                             int nrows, int ncols, int SH, int SW, float* __restrict__ canvas,
-                                                            uint8_t* __restrict__ cover) {
+                                                            uint8_t* __restrict__ cover, const float* __restrict__ win) {
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * G;
-    const int y = blockIdx.y;
     if (x >= SW) return;
-    const int i_lo = y >= ps ? (y - ps) / stride + 1 : 0;
-    const int i_hi = min(nrows - 1, y / stride);
-    const int j_lo = x >= ps ? (x - ps) / stride + 1 : 0;
-    const int j_hi = min(ncols - 1, x / stride);
-    float acc[CMAX][G];
+    for (int y = blockIdx.y; y < SH; y += gridDim.y) {
+        const int i_lo = y >= ps ? (y - ps) / stride + 1 : 0;
+        const int i_hi = min(nrows - 1, y / stride);
+        const int j_lo = x >= ps ? (x - ps) / stride + 1 : 0;
+        const int j_hi = min(ncols - 1, x / stride);
+        float acc[CMAX][G];
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c)
+        for (int c = 0; c < CMAX; ++c)
 #pragma unroll
-        for (int k = 0; k < G; ++k) acc[c][k] = 0.f;
-    float cnt = 0.f;
-    const size_t pp = static_cast<size_t>(ps) * ps;
-    for (int i = i_lo; i <= i_hi; ++i) {
-        const int ly = y - i * stride;
+            for (int k = 0; k < G; ++k) acc[c][k] = 0.f;
+        float cnt[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) cnt[k] = 0.f;
+        const size_t pp = static_cast<size_t>(ps) * ps;
+        for (int i = i_lo; i <= i_hi; ++i) {
+            const int ly = y - i * stride;
 #pragma unroll 4
-        for (int j = j_lo; j <= j_hi; ++j) {
-            const int p = __ldg(grid_map + i * ncols + j);
-            if (p < 0) continue;
-            const int lx = x - j * stride;
-            const float* src = preds + static_cast<size_t>(p) * C * pp + static_cast<size_t>(ly) * ps + lx;
+            for (int j = j_lo; j <= j_hi; ++j) {
+                const int p = __ldg(grid_map + i * ncols + j);
+                if (p < 0) continue;
+                const int lx = x - j * stride;
+                const float* src = preds + static_cast<size_t>(p) * C * pp + static_cast<size_t>(ly) * ps + lx;
+                if (win == nullptr) {
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c) {
-                if (c < C) {
-                    float v[G];
-                    ld_f<G>(src + c * pp, v);
+                    for (int c = 0; c < CMAX; ++c) {
+                        if (c < C) {
+                            float v[G];
+                            ld_f<G>(src + c * pp, v);
 #pragma unroll
-                    for (int k = 0; k < G; ++k) acc[c][k] = __fadd_rn(acc[c][k], v[k]);
+                            for (int k = 0; k < G; ++k) acc[c][k] = __fadd_rn(acc[c][k], v[k]);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < G; ++k) cnt[k] += 1.f;
+                } else {
+                    const float wy = __ldg(win + ly);
+                    float wgt[G];
+#pragma unroll
+                    for (int k = 0; k < G; ++k) wgt[k] = __fmul_rn(wy, __ldg(win + lx + k));
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) {
+                        if (c < C) {
+                            float v[G];
+                            ld_f<G>(src + c * pp, v);
+#pragma unroll
+                            for (int k = 0; k < G; ++k) acc[c][k] = __fadd_rn(acc[c][k], __fmul_rn(wgt[k], v[k]));
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < G; ++k) cnt[k] = __fadd_rn(cnt[k], wgt[k]);
                 }
             }
-            cnt += 1.f;
         }
-    }
-    const size_t plane = static_cast<size_t>(SH) * SW;
-    const size_t o = static_cast<size_t>(y) * SW + x;
+        const size_t plane = static_cast<size_t>(SH) * SW;
+        const size_t o = static_cast<size_t>(y) * SW + x;
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-        if (c < C) {
-            float v[G];
+        for (int c = 0; c < CMAX; ++c) {
+            if (c < C) {
+                float v[G];
 #pragma unroll
-            for (int k = 0; k < G; ++k) v[k] = cnt > 0.f ? __fdiv_rn(acc[c][k], cnt) : 0.f;
-            st_f<G>(canvas + c * plane + o, v);
+                for (int k = 0; k < G; ++k) v[k] = cnt[k] > 0.f ? __fdiv_rn(acc[c][k], cnt[k]) : 0.f;
+                st_f<G>(canvas + c * plane + o, v);
+            }
         }
-    }
-    uint8_t cv[G];
+        uint8_t cv[G];
 #pragma unroll
-    for (int k = 0; k < G; ++k) cv[k] = cnt > 0.f ? 1 : 0;
-    st_b<G>(cover + o, cv);
+        for (int k = 0; k < G; ++k) cv[k] = cnt[k] > 0.f ? 1 : 0;
+        st_b<G>(cover + o, cv);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- debug / noise helpers
+// Number of fp16 elements of an NHWC activation view that sit at the saturation value of the epilogues' cvt.rn.satfinite
+// (|v| = 65504) or are not finite.  Measurement aid: a clamp in a conv epilogue leaves exactly this footprint.
+__global__ void saturation_count_kernel(const __half* __restrict__ src, int cpitch, int C, size_t npix,
+                                        unsigned long long* __restrict__ out) {
+    unsigned long long n = 0;
+    const size_t total = npix * C;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t px = i / C;
+        const int c = static_cast<int>(i - px * C);
+        const uint16_t bits = __half_as_ushort(src[px * cpitch + c]) & 0x7FFFu;
+        n += bits >= 0x7BFFu ? 1u : 0u;
+    }
+    n = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(n));
+    if ((threadIdx.x & 31) == 0 && n != 0) atomicAdd(out, n);
 }
 
 }  // namespace s1s2

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -65,7 +66,11 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
     float mx = 0.f;
     if (i < total) {
         const int pix = static_cast<int>(i - static_cast<size_t>(b) * HW);
-        const float t = t_idx != nullptr ? static_cast<float>(t_idx[b]) : t_const;
+        float t = t_const;
+        if (t_idx != nullptr) {         // outside the fp16-exact integer range the time planes would be silently rounded:
+            const int64_t ti = t_idx[b];                    // poison the call instead (NaN planes -> NaN output)
+            t = (ti >= 0 && ti <= 2048) ? static_cast<float>(ti) : __int_as_float(0x7FC00000);
+        }
         float xv[4], cv[4], hi[4], lo[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -90,6 +95,30 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
     }
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
     if ((threadIdx.x & 31) == 0 && wmax != 0u) atomicMax(amax + b, wmax);
+}
+
+// Unit-normal initial noise keyed by GLOBAL patch id (scene sharding: the draw of a patch does not depend on the rank or
+// batch slot it lands in).  Philox4x32-10, key = seed, counter = (element / 4, id lo, id hi, tag); two Box-Muller pairs.
+__global__ void __launch_bounds__(256) patch_noise_kernel(const int64_t* __restrict__ ids, uint32_t seed_lo, uint32_t seed_hi,
+                                                          size_t elems4, float4* __restrict__ out) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= elems4) return;
+    const uint64_t id = static_cast<uint64_t>(ids[blockIdx.y]);
+    uint32_t u[4];
+    philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(id), static_cast<uint32_t>(id >> 32), 0x4E4F4953u, seed_lo,
+                  seed_hi, u);
+    float z[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float a = (static_cast<float>(u[2 * k]) + 0.5f) * 2.3283064365386963e-10f;        // (0, 1)
+        const float b = (static_cast<float>(u[2 * k + 1]) + 0.5f) * 2.3283064365386963e-10f;
+        const float r = sqrtf(-2.f * logf(a));
+        float sn, cs;
+        sincospif(2.f * b, &sn, &cs);
+        z[2 * k] = r * cs;
+        z[2 * k + 1] = r * sn;
+    }
+    out[blockIdx.y * elems4 + i] = make_float4(z[0], z[1], z[2], z[3]);
 }
 
 // Conv2d weight OIHW f32 -> [cout][tap][cin] fp16 (K-major rows for the UMMA B operand).
@@ -170,7 +199,7 @@ CUtensorMapSwizzle swizzle_for(int kbox) {
 }
 
 // ---------------------------------------------------------------------------------------------- layers
-enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_PX_STORE, K_PX_HEAD32, K_HSTORE, K_HPOOL, K_HSTORE256, K_HPOOL256, K_HINC, K_HC96IN, K_COUNT };
+enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_PX_STORE, K_PX_HEAD32, K_HSTORE, K_HPOOL, K_HSTORE256, K_HPOOL256, K_HINC, K_HC96IN, K_HSTORE96, K_HPOOL96, K_HHEAD96, K_COUNT };
 
 struct KernelInfo {
     void (*fn)(const ConvParams);
@@ -239,6 +268,13 @@ struct KernelTable {
         t[K_PX_HEAD32] = make_px_kernel<32, 4, MODE_HEAD, 3, 3>();        // same with exact 32-channel chunks, one kernel row per
                                                                           // stage, three halo slots (default)
         t[K_HEAD] = make_kernel<96, 32, 3, 6, MODE_HEAD>();     // conv1.2 + outc + scheduler
+        // Cout-on-N tiles of 96 columns, three taps per stage (one tcgen05.mma of M = 256, N = 96, K = 16 is 48 cycles, so a
+        // one-tap stage of four would sit under the ~300-cycle issue loop).  Used (a) when a layer has too few N = 192 / 256
+        // tiles to fill the 74 CTA pairs (small batches: see pick_variant) and (b) as the A/B partner of the pixels-on-N
+        // kernels for the Cout = 96 layers (S1S2_C1_UMMA=1).
+        t[K_HSTORE96] = make_kernel<96, 64, 1, 6, MODE_STORE, 2, true, false, 1, 3>();
+        t[K_HPOOL96] = make_kernel<96, 64, 1, 6, MODE_POOL, 2, true, false, 1, 3>();
+        t[K_HHEAD96] = make_kernel<96, 32, 1, 3, MODE_HEAD, 2, true, false, 1, 9>();   // conv1.2: exact 32-channel chunks, nine taps per stage
     }
 };
 const KernelInfo* kernel_table() {
@@ -263,6 +299,10 @@ struct Layer {
     __half* w = nullptr;
     float* bias = nullptr;
     ConvParams p;
+    // Alternative tilings of the same layer (same weights, same arithmetic per output element): narrower N tiles that
+    // fill the 74 CTA pairs when the batch is small.  pick_variant chooses per launch.
+    struct Alt { KernelId kid; ConvParams p; };
+    std::vector<Alt> alts;
 };
 
 struct View {
@@ -289,8 +329,12 @@ struct s1s2_handle {
     uint32_t* amax = nullptr;     // [2][max_batch] float bits of max|x_t| per patch, ping-pong across model calls
     float head_w[kHeadOut * kHeadIn];
     float head_b[kHeadOut];
-    // staging for s1s2_sample_host
-    float *st_cond = nullptr, *st_x = nullptr, *st_out = nullptr;
+    // staging for s1s2_sample_host / s1s2_sample_host_stream (two sets: batch i+1 uploads while batch i computes)
+    float *st_cond[2] = {nullptr, nullptr}, *st_x[2] = {nullptr, nullptr}, *st_out[2] = {nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_out = nullptr;                  // copy streams of the pipelined host entry
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
+                ev_out[2] = {nullptr, nullptr}, ev_entry = nullptr;
+    unsigned long long* sat_counts = nullptr;                      // [views] scratch of s1s2_debug_saturation_count
 };
 
 namespace {
@@ -325,14 +369,40 @@ int dmalloc(s1s2_handle* h, void** p, size_t bytes, std::string* err) {
     return S1S2_OK;
 }
 
+// Timing events owned for the duration of one API call.
+struct EventSet {
+    std::vector<cudaEvent_t> ev;
+    ~EventSet() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    int create(int n, std::string* err) {
+        ev.reserve(n);
+        for (int i = 0; i < n; ++i) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            ev.push_back(e);
+        }
+        return S1S2_OK;
+    }
+    cudaEvent_t operator[](int i) const { return ev[i]; }
+};
+
+// One-time per-device settings of the handle-less entry points (the attributes live in the device's context).
+struct DeviceOnce {
+    std::mutex mu;
+    bool metrics_attr[64] = {};
+    bool pool_keep[64] = {};
+};
+DeviceOnce& device_once() {
+    static DeviceOnce d;
+    return d;
+}
+
 // conv_px_kernel: pixels (16 x 16 tile of one image) on N, weight rows on M.
-int build_px_params(s1s2_handle* h, Layer& L, const KernelInfo& k, EncodeTiledFn enc, std::string* err) {
+int build_px_params(s1s2_handle* h, Layer& L, const KernelInfo& k, ConvParams& p, EncodeTiledFn enc, std::string* err) {
     const int Hl = h->H >> L.level, Wl = h->W >> L.level;
     if (Hl % 16 != 0 || Wl % 8 != 0 || L.cout > 128 || L.taps_w != 3) {
         set_err(err, "layer %s: geometry does not fit the pixels-on-N kernel", L.name);
         return S1S2_ERR_INVALID;
     }
-    ConvParams& p = L.p;
     memset(&p, 0, sizeof(p));
     const CUtensorMapSwizzle sw = swizzle_for(k.kbox);
     {   // activations: (C, W, H, N), box (kbox, 16, 16, 1); channels past Cin are zero-filled
@@ -381,15 +451,15 @@ int build_px_params(s1s2_handle* h, Layer& L, const KernelInfo& k, EncodeTiledFn
     return S1S2_OK;
 }
 
-int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
-    const KernelInfo& k = kernel_table()[L.kid];
+int build_layer_params(s1s2_handle* h, Layer& L, KernelId kid, ConvParams& p, std::string* err) {
+    const KernelInfo& k = kernel_table()[kid];
     EncodeTiledFn enc = get_encode_fn();
     if (enc == nullptr) {
         set_err(err, "cuTensorMapEncodeTiled is not available from this driver");
         return S1S2_ERR_CUDA;
     }
     const int Hl = h->H >> L.level, Wl = h->W >> L.level;
-    if (k.px) return build_px_params(h, L, k, enc, err);
+    if (k.px) return build_px_params(h, L, k, p, enc, err);
     TileGeom g = tile_geom(Hl, Wl);
     if (k.halo) {            // 8 wide x 16 tall tile of one image; partial tiles are zero-filled on load, clipped on store
         g.tw_log2 = 3;
@@ -404,7 +474,6 @@ int build_layer_params(s1s2_handle* h, Layer& L, std::string* err) {
         set_err(err, "layer %s: geometry does not fit kernel (cin %d, N %d)", L.name, L.cin, L.ntot);
         return S1S2_ERR_INVALID;
     }
-    ConvParams& p = L.p;
     memset(&p, 0, sizeof(p));
     {   // activations: (C, W, H, N), box (kbox, tw, th, tn)
         cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cin), static_cast<cuuint64_t>(Wl), static_cast<cuuint64_t>(Hl),
@@ -517,32 +586,67 @@ int launch_conv(const KernelInfo& k, int grid, const ConvParams& p, cudaStream_t
     return S1S2_OK;
 }
 
-int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, cudaStream_t st, std::string* err) {
-    const KernelInfo& k = kernel_table()[L.kid];
-    ConvParams& p = L.p;
-    if (k.px) {
-        p.B = B;
-        p.amax_in = amax_in;
-        const int tiles = (p.W >> 3) * ((p.H + 31) >> 5) * B;
-        int rc = launch_conv(k, tiles < h->num_sms ? tiles : h->num_sms, p, st, err);
-        if (rc != S1S2_OK) return rc;
-        ++h->launches;
-        return S1S2_OK;
-    }
+// CTA-pair kernels: group tiles (2 M tiles x 1 N tile) of a launch at batch B.
+int group_tiles_of(const KernelInfo& k, const ConvParams& p, int B) {
     const int tn = 128 >> (p.tw_log2 + p.th_log2);
+    const int m_tiles = p.tiles_x * p.tiles_y * ((B + tn - 1) / tn);
+    return ((m_tiles + k.ctas - 1) / k.ctas) * p.num_n_tiles;
+}
+
+// Which tiling of the layer runs at batch B.  A launch takes waves x (time of one group tile); the K loop of a tile is
+// N/2 cycles per tcgen05.mma (B300_MICROARCH.md: max(M,128) * N / (256 * cta_group)), so the cost of a variant is
+// waves * (BLOCK_N + c), c = the per-tile fixed part (accumulator hand-over, epilogue tail) in the same unit.  At batch 64
+// every layer has hundreds of tiles and the widest tile wins (least weight traffic per flop); at batch 1 the 64 x 64
+// layers have 32 M tiles and N = 96 / 192 tiles are what fills the 74 CTA pairs.  Every variant accumulates each output
+// element over (chunk, tap, k) in the same order, so the choice never changes a bit of the result.
+const Layer::Alt* pick_variant(const s1s2_handle* h, const Layer& L, int B) {
+    if (L.alts.empty()) return nullptr;
+    const KernelInfo* kt = kernel_table();
+    auto cost = [&](const KernelInfo& k, const ConvParams& p) {
+        const int slots = h->num_sms / k.ctas;
+        const int waves = (group_tiles_of(k, p, B) + slots - 1) / slots;
+        return static_cast<long>(waves) * (k.block_n + 24);
+    };
+    long best = cost(kt[L.kid], L.p);
+    const Layer::Alt* pick = nullptr;
+    for (const Layer::Alt& a : L.alts) {          // alternates are listed widest first: ties keep the wider tile
+        const long c = cost(kt[a.kid], a.p);
+        if (c < best) { best = c; pick = &a; }
+    }
+    return pick;
+}
+
+int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, uint32_t* amax_zero, cudaStream_t st,
+                 std::string* err) {
+    const Layer::Alt* alt = (L.p.perf_mode == 0) ? pick_variant(h, L, B) : nullptr;
+    const KernelInfo& k = kernel_table()[alt != nullptr ? alt->kid : L.kid];
+    ConvParams p = alt != nullptr ? alt->p : L.p;          // per-launch copy: the kernel takes it by value anyway
     p.B = B;
-    p.num_m_tiles = p.tiles_x * p.tiles_y * ((B + tn - 1) / tn);
     p.amax_in = amax_in;
-    const int group_tiles = ((p.num_m_tiles + k.ctas - 1) / k.ctas) * p.num_n_tiles;   // one CTA group per (ctas M tiles, 1 N tile)
-    const int clusters = group_tiles < h->num_sms / k.ctas ? group_tiles : h->num_sms / k.ctas;
-    int rc = launch_conv(k, k.ctas * clusters, p, st, err);                // __cluster_dims__(ctas, 1, 1)
+    p.amax_zero = amax_zero;
+    int grid;
+    if (k.px) {
+        const int tiles = (p.W >> 3) * ((p.H + 31) >> 5) * B;
+        grid = tiles < h->num_sms ? tiles : h->num_sms;
+    } else {
+        const int tn = 128 >> (p.tw_log2 + p.th_log2);
+        p.num_m_tiles = p.tiles_x * p.tiles_y * ((B + tn - 1) / tn);
+        const int group_tiles = group_tiles_of(k, p, B);                    // one CTA group per (ctas M tiles, 1 N tile)
+        const int clusters = group_tiles < h->num_sms / k.ctas ? group_tiles : h->num_sms / k.ctas;
+        grid = k.ctas * clusters;                                           // __cluster_dims__(ctas, 1, 1)
+    }
+    int rc = launch_conv(k, grid, p, st, err);
     if (rc != S1S2_OK) return rc;
     ++h->launches;
     return S1S2_OK;
 }
 
-int run_network(s1s2_handle* h, int B, const HeadParams& head_io, const uint32_t* amax_in, cudaStream_t st,
-                std::string* err) {
+// `amax_zero` ([B] or nullptr): cleared by the first layer's kernel for the head of THIS call to reduce max|x_next| into --
+// its last readers were the kernels of the previous call, complete by the time any kernel of this call passes
+// griddepcontrol.wait.  (A cudaMemsetAsync between calls would put a memset node between conv1.2 and the next inc.0 and
+// break the programmatic-dependent-launch chain once per model call.)
+int run_network(s1s2_handle* h, int B, const HeadParams& head_io, const uint32_t* amax_in, uint32_t* amax_zero,
+                cudaStream_t st, std::string* err) {
     for (size_t i = 0; i < h->layers.size(); ++i) {
         Layer& L = h->layers[i];
         if (kernel_table()[L.kid].mode == MODE_HEAD) {
@@ -558,7 +662,7 @@ int run_network(s1s2_handle* h, int B, const HeadParams& head_io, const uint32_t
             hp.amax_out = head_io.amax_out;
             hp.step = head_io.step;
         }
-        int rc = launch_layer(h, L, B, amax_in, st, err);
+        int rc = launch_layer(h, L, B, amax_in, L.first ? amax_zero : nullptr, st, err);
         if (rc != S1S2_OK) return rc;
     }
     return S1S2_OK;
@@ -582,7 +686,7 @@ int check_batch(s1s2_handle* h, int B) {
 // ================================================================================================ C ABI
 extern "C" {
 
-int s1s2_abi_version(void) { return 2; }   // 2: s1s2_patch_metrics rows grew from 8 to 24 doubles (per-channel sums)
+int s1s2_abi_version(void) { return 3; }   // 3: + sample_host_stream, patch_noise, stitch_weighted, debug_saturation_count
 
 const char* s1s2_global_error(void) { return g_error.c_str(); }
 const char* s1s2_last_error(const s1s2_handle* h) { return h != nullptr ? h->err.c_str() : g_error.c_str(); }
@@ -658,13 +762,28 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     }
     {
         const size_t img = static_cast<size_t>(max_batch) * 4 * P0 * sizeof(float);
+        for (int k = 0; k < 2; ++k) {
+            float** slots[3] = {&h->st_cond[k], &h->st_x[k], &h->st_out[k]};
+            for (float** slot : slots) {
+                void* p;
+                if (dmalloc(h, &p, img, err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
+                *slot = static_cast<float*>(p);
+            }
+        }
         void* p;
-        if (dmalloc(h, &p, img, err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
-        h->st_cond = static_cast<float*>(p);
-        if (dmalloc(h, &p, img, err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
-        h->st_x = static_cast<float*>(p);
-        if (dmalloc(h, &p, img, err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
-        h->st_out = static_cast<float*>(p);
+        if (dmalloc(h, &p, sizeof(unsigned long long) * 32, err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
+        h->sat_counts = static_cast<unsigned long long*>(p);
+        bool ok = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming) == cudaSuccess;
+        for (int k = 0; k < 2 && ok; ++k)
+            for (cudaEvent_t* e : {&h->ev_in[k], &h->ev_packed[k], &h->ev_done[k], &h->ev_out[k]})
+                ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            set_err(err, "stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            s1s2_destroy(h);
+            return S1S2_ERR_CUDA;
+        }
     }
 
     auto add = [&](const char* name, KernelId kid, int level, int cin, int ntot, int cout, int taps, const __half* src,
@@ -714,8 +833,17 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     }
     if (getenv("S1S2_NO_PX") == nullptr) {       // default: pixels-on-N kernels for the Cout = 96 full-resolution layers
         for (Layer& L : h->layers) {
-            if (L.kid == K_N96) L.kid = K_PX_STORE;
-            if (L.kid == K_HEAD) L.kid = K_PX_HEAD32;
+            if (L.kid == K_N96) L.kid = getenv("S1S2_C10_UMMA") != nullptr ? K_HSTORE96 : K_PX_STORE;     // A/B: Cout on N, halo, TPS 3
+            if (L.kid == K_HEAD) L.kid = getenv("S1S2_C12_UMMA") != nullptr ? K_HHEAD96 : K_PX_HEAD32;    // A/B: same, TPS 9
+        }
+    }
+    if (getenv("S1S2_NO_ALTS") == nullptr) {     // narrower tilings for small batches (pick_variant), widest first
+        for (Layer& L : h->layers) {
+            auto alt = [&](KernelId kid) { if (L.ntot % kernel_table()[kid].block_n == 0) L.alts.push_back({kid, ConvParams()}); };
+            if (L.kid == K_HSTORE256) { alt(K_HSTORE); alt(K_HSTORE96); }
+            else if (L.kid == K_HPOOL256) { alt(K_HPOOL); alt(K_HPOOL96); }
+            else if (L.kid == K_HSTORE) alt(K_HSTORE96);
+            else if (L.kid == K_HPOOL) alt(K_HPOOL96);
         }
     }
     for (Layer& L : h->layers) {
@@ -725,7 +853,9 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
         L.w = static_cast<__half*>(p);
         if (dmalloc(h, &p, static_cast<size_t>(L.ntot) * sizeof(float), err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
         L.bias = static_cast<float*>(p);
-        int rc = build_layer_params(h, L, err);
+        int rc = build_layer_params(h, L, L.kid, L.p, err);
+        for (Layer::Alt& a : L.alts)
+            if (rc == S1S2_OK) rc = build_layer_params(h, L, a.kid, a.p, err);
         if (rc != S1S2_OK) { s1s2_destroy(h); return rc; }
     }
     // views for s1s2_debug_activation: name = the oracle's tap key
@@ -749,6 +879,12 @@ void s1s2_destroy(s1s2_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
+    for (int k = 0; k < 2; ++k)
+        for (cudaEvent_t e : {h->ev_in[k], h->ev_packed[k], h->ev_done[k], h->ev_out[k]})
+            if (e != nullptr) cudaEventDestroy(e);
+    if (h->ev_entry != nullptr) cudaEventDestroy(h->ev_entry);
+    if (h->s_in != nullptr) cudaStreamDestroy(h->s_in);
+    if (h->s_out != nullptr) cudaStreamDestroy(h->s_out);
     delete h;
 }
 
@@ -836,12 +972,12 @@ int s1s2_forward(s1s2_handle* h, const float* xt_and_cond, const int64_t* t_idx,
     memset(&io, 0, sizeof(io));
     io.pred_out = out;
     io.step.kind = STEP_NONE;
-    return run_network(h, B, io, h->amax, st, err);
+    return run_network(h, B, io, h->amax, nullptr, st, err);
 }
 
-int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond, const float* x_init,
-                float init_scale, const float* step_noise, float* out, float* tap_pred, float* tap_x, int B,
-                void* stream) {
+static int sample_impl(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond, const float* x_init,
+                       float init_scale, const float* step_noise, float* out, float* tap_pred, float* tap_x, int B,
+                       void* stream, cudaEvent_t after_pack) {
     int rc = check_batch(h, B);
     if (rc != S1S2_OK) return rc;
     std::string* err = &h->err;
@@ -879,10 +1015,10 @@ int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float
         init_scale, out, h->xin16, h->amax, HW, total);
     CK(cudaGetLastError());
     ++h->launches;
+    if (after_pack != nullptr) CK(cudaEventRecord(after_pack, st));       // cond / x_init are not read past this point
     for (int i = 0; i < n_steps; ++i) {
         uint32_t* amax_cur = h->amax + static_cast<size_t>(i & 1) * h->max_batch;
         uint32_t* amax_nxt = h->amax + static_cast<size_t>((i + 1) & 1) * h->max_batch;
-        CK(cudaMemsetAsync(amax_nxt, 0, sizeof(uint32_t) * B, st));   // last read by the previous call, now complete
         HeadParams io;
         memset(&io, 0, sizeof(io));
         io.amax_out = amax_nxt;
@@ -902,12 +1038,18 @@ int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float
         io.step.t_next = i + 1 < n_steps ? static_cast<float>(steps[i + 1].t) : 0.f;
         io.step.kind = steps[i].kind;
         io.step.flags = steps[i].flags;
-        rc = run_network(h, B, io, amax_cur, st, err);
+        rc = run_network(h, B, io, amax_cur, amax_nxt, st, err);
         if (rc != S1S2_OK) return rc;
         if (tap_x != nullptr)
             CK(cudaMemcpyAsync(tap_x + static_cast<size_t>(i) * img, out, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     return S1S2_OK;
+}
+
+int s1s2_sample(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond, const float* x_init,
+                float init_scale, const float* step_noise, float* out, float* tap_pred, float* tap_x, int B,
+                void* stream) {
+    return sample_impl(h, steps, n_steps, cond, x_init, init_scale, step_noise, out, tap_pred, tap_x, B, stream, nullptr);
 }
 
 int s1s2_set_noise_seed(s1s2_handle* h, uint64_t seed, uint32_t patch_base) {
@@ -919,22 +1061,56 @@ int s1s2_set_noise_seed(s1s2_handle* h, uint64_t seed, uint32_t patch_base) {
 
 int s1s2_sample_host(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond_host,
                      const float* x_init_host, float init_scale, float* out_host, int B, void* stream) {
-    int rc = check_batch(h, B);
+    return s1s2_sample_host_stream(h, steps, n_steps, cond_host, x_init_host, init_scale, out_host, B, B, stream);
+}
+
+int s1s2_sample_host_stream(s1s2_handle* h, const s1s2_step* steps, int n_steps, const float* cond_host,
+                            const float* x_init_host, float init_scale, float* out_host, int N, int batch, void* stream) {
+    int rc = check_batch(h, batch);
     if (rc != S1S2_OK) return rc;
     std::string* err = &h->err;
-    if (cond_host == nullptr || x_init_host == nullptr || out_host == nullptr) {
-        h->err = "s1s2_sample_host: null pointer argument";
+    if (cond_host == nullptr || x_init_host == nullptr || out_host == nullptr || N < 0) {
+        h->err = "s1s2_sample_host_stream: null pointer argument / negative patch count";
         return S1S2_ERR_INVALID;
     }
+    if (N == 0) return S1S2_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
-    const size_t bytes = static_cast<size_t>(B) * 4 * h->H * h->W * sizeof(float);
-    CK(cudaMemcpyAsync(h->st_cond, cond_host, bytes, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->st_x, x_init_host, bytes, cudaMemcpyHostToDevice, st));
-    rc = s1s2_sample(h, steps, n_steps, h->st_cond, h->st_x, init_scale, nullptr, h->st_out, nullptr, nullptr, B, stream);
+    const size_t patch = static_cast<size_t>(4) * h->H * h->W;          // floats per patch
+    const int nb = (N + batch - 1) / batch;
+    // Three streams: uploads of batch i+1 (s_in) and the download of batch i-1 (s_out) run under the model calls of batch
+    // i (`stream`); two staging sets.  Set k is free for upload once the pack kernel of its previous occupant has run
+    // (cond / x_init are read nowhere else), and free for compute once that occupant's result has been downloaded.
+    CK(cudaEventRecord(h->ev_entry, st));
+    CK(cudaStreamWaitEvent(h->s_in, h->ev_entry, 0));
+    CK(cudaStreamWaitEvent(h->s_out, h->ev_entry, 0));
+    for (int i = 0; i < nb; ++i) {
+        const int k = i & 1;
+        const size_t lo = static_cast<size_t>(i) * batch;
+        const int Bi = static_cast<int>(static_cast<size_t>(N) - lo < static_cast<size_t>(batch) ? N - lo : batch);
+        const size_t bytes = static_cast<size_t>(Bi) * patch * sizeof(float);
+        if (i >= 2) CK(cudaStreamWaitEvent(h->s_in, h->ev_packed[k], 0));
+        CK(cudaMemcpyAsync(h->st_cond[k], cond_host + lo * patch, bytes, cudaMemcpyHostToDevice, h->s_in));
+        CK(cudaMemcpyAsync(h->st_x[k], x_init_host + lo * patch, bytes, cudaMemcpyHostToDevice, h->s_in));
+        CK(cudaEventRecord(h->ev_in[k], h->s_in));
+        CK(cudaStreamWaitEvent(st, h->ev_in[k], 0));
+        if (i >= 2) CK(cudaStreamWaitEvent(st, h->ev_out[k], 0));
+        rc = sample_impl(h, steps, n_steps, h->st_cond[k], h->st_x[k], init_scale, nullptr, h->st_out[k], nullptr, nullptr, Bi,
+                         stream, h->ev_packed[k]);
+        if (rc != S1S2_OK) break;
+        CK(cudaEventRecord(h->ev_done[k], st));
+        CK(cudaStreamWaitEvent(h->s_out, h->ev_done[k], 0));
+        CK(cudaMemcpyAsync(out_host + lo * patch, h->st_out[k], bytes, cudaMemcpyDeviceToHost, h->s_out));
+        CK(cudaEventRecord(h->ev_out[k], h->s_out));
+    }
+    // whatever happened above, leave no copy in flight on the side streams when returning
+    cudaError_t e1 = cudaStreamSynchronize(h->s_in), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(h->s_out);
     if (rc != S1S2_OK) return rc;
-    CK(cudaMemcpyAsync(out_host, h->st_out, bytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    for (cudaError_t e : {e1, e2, e3})
+        if (e != cudaSuccess) {
+            set_err(err, "s1s2_sample_host_stream: %s", cudaGetErrorString(e));
+            return S1S2_ERR_CUDA;
+        }
     return S1S2_OK;
 }
 
@@ -986,22 +1162,20 @@ int s1s2_debug_loop_layer(s1s2_handle* h, int B, int layer, int reps, int perf_m
         hp.x_t = nullptr; hp.pred_out = nullptr; hp.noise = nullptr; hp.xin16 = nullptr; hp.amax_out = nullptr;
         hp.step.kind = STEP_NONE;
     }
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    EventSet ev;                                   // destroyed on every return path
+    if ((rc = ev.create(2, err)) != S1S2_OK) return rc;
     L.p.perf_mode = perf_mode;
-    rc = launch_layer(h, L, B, nullptr, st, err);      // warm-up
-    CK(cudaEventRecord(e0, st));
-    for (int r = 0; r < reps && rc == S1S2_OK; ++r) rc = launch_layer(h, L, B, nullptr, st, err);
-    CK(cudaEventRecord(e1, st));
+    rc = launch_layer(h, L, B, nullptr, nullptr, st, err);      // warm-up
+    cudaError_t ce = cudaEventRecord(ev[0], st);
+    for (int r = 0; r < reps && rc == S1S2_OK; ++r) rc = launch_layer(h, L, B, nullptr, nullptr, st, err);
+    if (ce == cudaSuccess) ce = cudaEventRecord(ev[1], st);
     L.p.perf_mode = 0;
     if (rc != S1S2_OK) return rc;
+    CK(ce);
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
+    CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
     *ms_out = ms / reps;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return S1S2_OK;
 }
 
@@ -1018,8 +1192,8 @@ int s1s2_profile_layers(s1s2_handle* h, int B, int reps, float* ms_out, int n_ou
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
-    std::vector<cudaEvent_t> ev(static_cast<size_t>(reps) * (nl + 1));
-    for (auto& e : ev) CK(cudaEventCreate(&e));
+    EventSet ev;                                   // destroyed on every return path
+    if ((rc = ev.create(reps * (nl + 1), err)) != S1S2_OK) return rc;
     HeadParams io;
     memset(&io, 0, sizeof(io));
     io.step.kind = STEP_NONE;
@@ -1034,7 +1208,7 @@ int s1s2_profile_layers(s1s2_handle* h, int B, int reps, float* ms_out, int n_ou
                 hp.step = io.step;
             }
             CK(cudaEventRecord(ev[r * (nl + 1) + i], st));
-            rc = launch_layer(h, L, B, nullptr, st, err);
+            rc = launch_layer(h, L, B, nullptr, nullptr, st, err);
             if (rc != S1S2_OK) return rc;
         }
         CK(cudaEventRecord(ev[r * (nl + 1) + nl], st));
@@ -1049,7 +1223,6 @@ int s1s2_profile_layers(s1s2_handle* h, int B, int reps, float* ms_out, int n_ou
         }
         ms_out[i] = static_cast<float>(acc / reps);
     }
-    for (auto& e : ev) cudaEventDestroy(e);
     return S1S2_OK;
 }
 
@@ -1104,11 +1277,14 @@ int s1s2_patch_metrics(int device, const float* pred, const float* gt, const uin
     const bool stream_ok = vec && C <= kMsC && HW % kMsChunk == 0 && (mask == nullptr || aligned_to(mask, 16)) &&
                            getenv("S1S2_METRICS_REGPATH") == nullptr;
     if (stream_ok) {                   // bulk-copy ring + 16 consumer warps (the usual 256 x 256 x 4 geometry)
-        static bool attr_set[64] = {};                         // per device (the attribute lives in the device's context)
-        if (device < 0 || device >= 64 || !attr_set[device]) {
-            CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(patch_metrics_stream_kernel),
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytes));
-            if (device >= 0 && device < 64) attr_set[device] = true;
+        {
+            DeviceOnce& once = device_once();
+            std::lock_guard<std::mutex> lock(once.mu);
+            if (device < 0 || device >= 64 || !once.metrics_attr[device]) {
+                CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(patch_metrics_stream_kernel),
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytes));
+                if (device >= 0 && device < 64) once.metrics_attr[device] = true;
+            }
         }
         patch_metrics_stream_kernel<<<N, kMsThreads, kMsSmemBytes, st>>>(pred, gt, mask, C, HW, out);
     } else if (vec && C <= 4) patch_metrics_kernel<4, 4><<<N, kMetricsThreads, 0, st>>>(pred, gt, mask, C, HW, out);
@@ -1120,6 +1296,11 @@ int s1s2_patch_metrics(int device, const float* pred, const float* gt, const uin
 
 int s1s2_stitch(int device, const float* preds, const int32_t* origins, int N, int C, int ps, int stride, int SH, int SW,
                 float* canvas, uint8_t* cover, void* stream) {
+    return s1s2_stitch_weighted(device, preds, origins, N, C, ps, stride, SH, SW, nullptr, canvas, cover, stream);
+}
+
+int s1s2_stitch_weighted(int device, const float* preds, const int32_t* origins, int N, int C, int ps, int stride, int SH,
+                         int SW, const float* window, float* canvas, uint8_t* cover, void* stream) {
     std::string* err = &g_error;
     if (preds == nullptr || origins == nullptr || canvas == nullptr || cover == nullptr || N < 0 || C < 1 || C > kStitchMaxC ||
         ps < 1 || stride < 1 || ps > SH || ps > SW) {
@@ -1131,34 +1312,91 @@ int s1s2_stitch(int device, const float* preds, const int32_t* origins, int N, i
     const int nrows = (SH - ps) / stride + 1, ncols = (SW - ps) / stride + 1;
     {   // keep the stream-ordered pool's memory across synchronisations (the default threshold of 0 hands it back to the
         // driver at every sync, which turns the small scratch allocation below into a ~0.5 ms driver call per stitch)
-        static bool pool_set[64] = {};
-        if (device >= 0 && device < 64 && !pool_set[device]) {
+        DeviceOnce& once = device_once();
+        std::lock_guard<std::mutex> lock(once.mu);
+        if (device >= 0 && device < 64 && !once.pool_keep[device]) {
             cudaMemPool_t pool;
             if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
                 uint64_t keep = 64ull << 20;
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
             }
-            pool_set[device] = true;
+            once.pool_keep[device] = true;
         }
     }
     int32_t* grid_map = nullptr;
     CK(cudaMallocAsync(reinterpret_cast<void**>(&grid_map), sizeof(int32_t) * nrows * ncols, st));
-    CK(cudaMemsetAsync(grid_map, 0xFF, sizeof(int32_t) * nrows * ncols, st));
-    if (N > 0) {
+    cudaError_t e = cudaMemsetAsync(grid_map, 0xFF, sizeof(int32_t) * nrows * ncols, st);
+    if (e == cudaSuccess && N > 0) {
         stitch_map_kernel<<<(N + 255) / 256, 256, 0, st>>>(origins, N, stride, nrows, ncols, grid_map);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        const unsigned gy = static_cast<unsigned>(SH < 65535 ? SH : 65535);       // rows beyond that: the kernel strides over y
+        if (SW % 4 == 0 && ps % 4 == 0 && stride % 4 == 0 && aligned_to(preds, 16) && aligned_to(canvas, 16) && aligned_to(cover, 4)) {
+            dim3 grid((SW / 4 + 127) / 128, gy);
+            if (C <= 4) stitch_gather_kernel<4, 4><<<grid, 128, 0, st>>>(preds, grid_map, C, ps, stride, nrows, ncols, SH, SW, canvas, cover, window);
+            else stitch_gather_kernel<4, kStitchMaxC><<<grid, 128, 0, st>>>(preds, grid_map, C, ps, stride, nrows, ncols, SH, SW, canvas, cover, window);
+        } else {
+            dim3 grid((SW + 127) / 128, gy);
+            stitch_gather_kernel<1, kStitchMaxC><<<grid, 128, 0, st>>>(preds, grid_map, C, ps, stride, nrows, ncols, SH, SW, canvas, cover, window);
+        }
+        e = cudaGetLastError();
+    }
+    const cudaError_t ef = cudaFreeAsync(grid_map, st);        // on every path: stream-ordered, after whatever was enqueued
+    CK(e);
+    CK(ef);
+    return S1S2_OK;
+}
+
+int s1s2_patch_noise(int device, uint64_t seed, const int64_t* patch_ids, int N, int64_t elems_per_patch, float* out,
+                     void* stream) {
+    std::string* err = &g_error;
+    if (N == 0) return S1S2_OK;
+    if (patch_ids == nullptr || out == nullptr || N < 0 || N > 65535 || elems_per_patch < 4 || elems_per_patch % 4 != 0 ||
+        !aligned_to(out, 16)) {
+        set_err(err, "s1s2_patch_noise: bad argument (N %d (<= 65535 per call), %lld elements per patch (multiple of 4), "
+                     "out 16-byte aligned)", N, static_cast<long long>(elems_per_patch));
+        return S1S2_ERR_INVALID;
+    }
+    CK(cudaSetDevice(device));
+    const size_t e4 = static_cast<size_t>(elems_per_patch / 4);
+    dim3 grid(static_cast<unsigned>((e4 + 255) / 256), static_cast<unsigned>(N));
+    patch_noise_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(patch_ids, static_cast<uint32_t>(seed),
+                                                                            static_cast<uint32_t>(seed >> 32), e4,
+                                                                            reinterpret_cast<float4*>(out));
+    CK(cudaGetLastError());
+    return S1S2_OK;
+}
+
+int s1s2_debug_saturation_count(s1s2_handle* h, int B, uint64_t* counts, int n_out, int* n_views, void* stream) {
+    int rc = check_batch(h, B);
+    if (rc != S1S2_OK) return rc;
+    std::string* err = &h->err;
+    const int nv = static_cast<int>(h->views.size());
+    if (n_views != nullptr) *n_views = nv;
+    if (counts == nullptr) return S1S2_OK;
+    if (n_out < nv || nv > 32) {
+        set_err(err, "s1s2_debug_saturation_count: n_out %d (need >= %d)", n_out, nv);
+        return S1S2_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->sat_counts, 0, sizeof(unsigned long long) * nv, st));
+    for (int i = 0; i < nv; ++i) {
+        const View& v = h->views[i];
+        const size_t npix = static_cast<size_t>(B) * (h->H >> v.level) * (h->W >> v.level);
+        saturation_count_kernel<<<h->num_sms * 4, 256, 0, st>>>(v.ptr, v.pitch, v.C, npix, h->sat_counts + i);
         CK(cudaGetLastError());
     }
-    if (SW % 4 == 0 && ps % 4 == 0 && stride % 4 == 0 && aligned_to(preds, 16) && aligned_to(canvas, 16) && aligned_to(cover, 4)) {
-        dim3 grid((SW / 4 + 127) / 128, SH);
-        if (C <= 4) stitch_gather_kernel<4, 4><<<grid, 128, 0, st>>>(preds, grid_map, C, ps, stride, nrows, ncols, SH, SW, canvas, cover);
-        else stitch_gather_kernel<4, kStitchMaxC><<<grid, 128, 0, st>>>(preds, grid_map, C, ps, stride, nrows, ncols, SH, SW, canvas, cover);
-    } else {
-        dim3 grid((SW + 127) / 128, SH);
-        stitch_gather_kernel<1, kStitchMaxC><<<grid, 128, 0, st>>>(preds, grid_map, C, ps, stride, nrows, ncols, SH, SW, canvas, cover);
-    }
-    CK(cudaGetLastError());
-    CK(cudaFreeAsync(grid_map, st));
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter width");
+    CK(cudaMemcpyAsync(counts, h->sat_counts, sizeof(uint64_t) * nv, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return S1S2_OK;
+}
+
+const char* s1s2_view_name(const s1s2_handle* h, int i) {
+    if (h == nullptr || i < 0 || i >= static_cast<int>(h->views.size())) return nullptr;
+    return h->views[i].name;
 }
 
 }  // extern "C"

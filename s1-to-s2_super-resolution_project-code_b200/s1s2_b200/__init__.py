@@ -7,8 +7,8 @@ There is no CPU / PyTorch fallback anywhere in this package.
 """
 from . import _lib, schedule, metrics, patch, patchio, samplers, scene  # noqa: F401
 from ._lib import S1S2Error  # noqa: F401
-from .model import UNetSmallB200  # noqa: F401
+from .model import UNetSmallB200, synthetic_checkpoint  # noqa: F401
 from .schedule import cosine_beta_schedule, linear_beta_schedule, make_schedule  # noqa: F401
 
-__all__ = ["UNetSmallB200", "S1S2Error", "schedule", "metrics", "patch", "samplers", "scene", "cosine_beta_schedule",
+__all__ = ["UNetSmallB200", "synthetic_checkpoint", "S1S2Error", "schedule", "metrics", "patch", "samplers", "scene", "cosine_beta_schedule",
            "linear_beta_schedule", "make_schedule"]

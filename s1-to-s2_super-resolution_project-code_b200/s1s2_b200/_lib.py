@@ -40,11 +40,17 @@ SIGNATURES = {
     "s1s2_set_noise_seed": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32]),
     "s1s2_sample_host": (C.c_int, [C.c_void_p, C.POINTER(Step), C.c_int, C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_void_p, C.c_int, C.c_void_p]),
+    "s1s2_sample_host_stream": (C.c_int, [C.c_void_p, C.POINTER(Step), C.c_int, C.c_void_p, C.c_void_p, C.c_float,
+                                          C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "s1s2_patch_noise": (C.c_int, [C.c_int, C.c_uint64, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "s1s2_debug_activation": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                         C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     "s1s2_profile_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int),
                                       C.c_void_p]),
     "s1s2_debug_loop_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
+    "s1s2_debug_saturation_count": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int),
+                                              C.c_void_p]),
+    "s1s2_view_name": (C.c_char_p, [C.c_void_p, C.c_int]),
     "s1s2_layer_name": (C.c_char_p, [C.c_void_p, C.c_int]),
     "s1s2_tile_extract": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -54,6 +60,8 @@ SIGNATURES = {
                                      C.c_void_p]),
     "s1s2_stitch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "s1s2_stitch_weighted": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -6,6 +6,8 @@
   python -m s1s2_b200.drivers ddim_sweep   ...   Evaluation/DDIM_Sweep.py --mode ddim_sweep (:387-416); --param v sweeps the
                                                  step counts of BASELINE.json's config 4 on the v model
   python -m s1s2_b200.drivers true_infer   ...   Evaluation_Updated/Evaluation_Pure_Generation.py --mode ddim --true_infer (:539-574)
+  python -m s1s2_b200.drivers night_demo   ...   the same script's --mode night_demo (:720-727): generation without a target;
+                                                 writes viz/NNN_night_pred.npy instead of the PNG panel
   python -m s1s2_b200.drivers limitation   ...   Evaluation/Limitation_Test.py run_eval (:273-400) and, with --param v,
                                                  Limitation_Test_v_Prediction.py run_eval (:258-372): batched DDPM / DDIM
                                                  sampling, dataset-level pixel-weighted MAE / MSE / PSNR, *_pred.npy / *_gt.npy
@@ -100,6 +102,15 @@ def _batches(args, files, device, workers=4):
                    [m.to(device) if m is not None else None for m in mask])
 
 
+def _batch_mask(mask, gt):
+    """u8/f32[B,H,W] mask of a batch of files; a file without a 'mask' key counts as all-valid (the reference handles
+    masks per file: masked_mae(..., mask=None) weighs every pixel)."""
+    if all(m is None for m in mask):
+        return None
+    ones = torch.ones((1,) + tuple(gt.shape[2:]), device=gt.device, dtype=torch.float32)
+    return torch.cat([m if m is not None else ones for m in mask], 0)
+
+
 def _mstd(a):
     t = torch.tensor(a)
     return t.mean().item(), t.std(unbiased=False).item()
@@ -130,9 +141,9 @@ def cmd_ddim(args, param):
         for lo, names, cond, gt, mask in _batches(args, files, device):
             noise = torch.cat([torch.randn_like(gt[i:i + 1]) for i in range(len(names))], 0)   # one draw per file
             x0 = _recon_batch(args, model, alpha_bar, cond, gt, noise, param, args.t_start, args.ddim_steps)
+            vals = metrics.patch_metrics(x0, gt, _batch_mask(mask, gt)).cpu()     # one fused pass + one copy per batch
             for i, fname in enumerate(names):
-                mae = metrics.masked_mae(x0[i:i + 1], gt[i:i + 1], mask[i])
-                mse = metrics.masked_mse(x0[i:i + 1], gt[i:i + 1], mask[i])
+                mae, mse = float(vals[i, 0]), float(vals[i, 1])
                 maes.append(mae); mses.append(mse)
                 row = [fname, args.t_start, args.ddim_steps] + ([args.ddim_eta] if param == "v" else [])
                 w.writerow(row + [f"{mae:.6f}", f"{mse:.6f}"])
@@ -162,9 +173,9 @@ def cmd_sweep(args):
                         noise.append(torch.randn_like(gt[i:i + 1]))
                     x0 = _recon_batch(args, model, alpha_bar, cond, gt, torch.cat(noise, 0), args.param, t_start, steps)
                     n_calls = steps if args.param == "eps" else len(schedule.grid_b(max(1, min(t_start, args.T - 1)), steps))
-                    for i in range(len(names)):
-                        maes.append(metrics.masked_mae(x0[i:i + 1], gt[i:i + 1], mask[i]))
-                        mses.append(metrics.masked_mse(x0[i:i + 1], gt[i:i + 1], mask[i]))
+                    vals = metrics.patch_metrics(x0, gt, _batch_mask(mask, gt)).cpu()
+                    maes += [float(v) for v in vals[:, 0]]
+                    mses += [float(v) for v in vals[:, 1]]
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
                 nb = (len(files) + args.batch - 1) // args.batch
@@ -190,8 +201,7 @@ def cmd_true_infer(args):
                     noise.append(torch.randn((1, gt.size(1), gt.size(2), gt.size(3)), device=device))
                 x0 = samplers.ddpm_ddim_generate(model, cond, alpha_bar, t_start=args.t_start, steps=args.ddim_steps,
                                                  noise=torch.cat(noise, 0))
-                mk = None if any(m is None for m in mask) else torch.cat(mask, 0)
-                vals = metrics.patch_metrics(x0, gt, mk).cpu()        # one fused pass + one copy for the whole batch
+                vals = metrics.patch_metrics(x0, gt, _batch_mask(mask, gt)).cpu()   # one fused pass + one copy per batch
                 for i in range(len(names)):
                     for k, col in (("mae", 0), ("mse", 1), ("psnr", 2), ("sam", 4), ("ergas", 5)):
                         per[i][k].append(float(vals[i, col]))
@@ -210,6 +220,24 @@ def cmd_true_infer(args):
         f.write(f"SAM  mean/std: {_mstd(agg['sam'])[0]:.4f} / {_mstd(agg['sam'])[1]:.4f}\n")
         f.write(f"ERGAS mean/std:{_mstd(agg['ergas'])[0]:.2f} / {_mstd(agg['ergas'])[1]:.2f}\n")
     print("[DONE] DDIM (TRUE-INFER)")
+
+
+def cmd_night_demo(args):
+    """Evaluation_Pure_Generation.py --mode night_demo (:720-727): pure generation from the conditioning alone (no target
+    is read) for the first max(1, --save_viz_n) files.  The reference renders a PNG panel per file; rendering is outside
+    the hot path, so the generated patch is saved as `viz/NNN_night_pred.npy` (f32[4,H,W]) next to the conditioning
+    `viz/NNN_night_cond.npy` -- what save_panel would have drawn."""
+    device, files, model, alpha_bar = _setup(args)
+    viz_dir = os.path.join(args.out_dir, "viz")
+    os.makedirs(viz_dir, exist_ok=True)
+    files = files[:max(1, args.save_viz_n)]
+    for lo, names, cond, gt, mask in _batches(args, files, device):
+        noise = torch.cat([torch.randn_like(gt[i:i + 1]) for i in range(len(names))], 0)      # one draw per file (:281)
+        x0 = samplers.ddpm_ddim_generate(model, cond, alpha_bar, t_start=args.t_start, steps=args.ddim_steps, noise=noise)
+        for i in range(len(names)):
+            np.save(os.path.join(viz_dir, f"{lo + i:03d}_night_pred.npy"), x0[i].cpu().numpy())
+            np.save(os.path.join(viz_dir, f"{lo + i:03d}_night_cond.npy"), cond[i].cpu().numpy())
+    print("[DONE] NIGHT_DEMO")
 
 
 def cmd_limitation(args):
@@ -240,7 +268,7 @@ def cmd_limitation(args):
             x_pred = samplers.ddpm_sample(model, cond, betas, alphas, alpha_bar, Ct, seed=args.seed + bi)
         else:
             x_pred = samplers.ddim_sample(model, cond, alphas, alpha_bar, Ct, steps=args.ddim_steps)
-        mk = None if any(m is None for m in mask) else torch.cat(mask, 0)
+        mk = _batch_mask(mask, gt)
         sums = metrics.channelwise_error_sums(x_pred, gt, mk)
         tot = sums if tot is None else tuple(a + b for a, b in zip(tot, sums))
         for b in range(len(names)):
@@ -280,7 +308,7 @@ def cmd_onestep(args):
     alpha_bar = alpha_bar.to(device)
     fn = samplers.one_step_recon_v if args.param == "v" else samplers.one_step_recon
     if args.param == "v":       # the v script's t=0 identity check is real (Onestep_v_Prediction.py:184-197)
-        mae0, mse0, _ = fn(model, x_gt, x_cond, alpha_bar, mask, 0, noise=torch.zeros_like(x_gt))
+        mae0, mse0, _ = fn(model, x_gt, x_cond, alpha_bar, mask, 0, noise=torch.zeros_like(x_gt), allow_t0=True)
     else:                       # the eps script's is vacuous: x0_hat_t0 = x_t0 (Onestep.py:139)
         mae0, mse0 = metrics.masked_mae(x_gt, x_gt, mask), metrics.masked_mse(x_gt, x_gt, mask)
     print(f"[t=0 identity] MAE={mae0:.6f}  MSE={mse0:.6f}  (should be ~0.0)")
@@ -332,7 +360,7 @@ def cmd_scene(args):
 
 def main(argv=None):
     ap = argparse.ArgumentParser("s1s2_b200 drivers")
-    ap.add_argument("cmd", choices=["onestep", "ddim", "ddim_v", "ddim_sweep", "true_infer", "limitation", "scene"])
+    ap.add_argument("cmd", choices=["onestep", "ddim", "ddim_v", "ddim_sweep", "true_infer", "night_demo", "limitation", "scene"])
     ap.add_argument("--patch_dir")
     ap.add_argument("--ckpt")
     ap.add_argument("--out_dir", required=True)
@@ -348,6 +376,7 @@ def main(argv=None):
     ap.add_argument("--t_start_grid", default="300,200,150,100")
     ap.add_argument("--ddim_steps_grid", default="10,20,50,100")
     ap.add_argument("--true_infer", action="store_true")
+    ap.add_argument("--save_viz_n", type=int, default=6)
     # Limitation_Test*.py flags (the v script's --t_start is --lim_t_start here: default None = start from T-1)
     ap.add_argument("--mode", default="ddim", choices=["ddpm", "ddim"])
     ap.add_argument("--time_schedule", default="cosine", choices=["cosine", "linear"])
@@ -376,6 +405,8 @@ def main(argv=None):
         cmd_sweep(args)
     elif args.cmd == "true_infer":
         cmd_true_infer(args)
+    elif args.cmd == "night_demo":
+        cmd_night_demo(args)
     elif args.cmd == "limitation":
         cmd_limitation(args)
     else:

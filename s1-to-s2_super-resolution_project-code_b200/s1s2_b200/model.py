@@ -50,6 +50,16 @@ class _Engine:
             pass
 
 
+def synthetic_checkpoint(seed: int, in_ch: int = 8, out_ch: int = 4, base_ch: int = 96):
+    """state_dict of a freshly initialised network under ``torch.manual_seed(seed)`` -- the stand-in for the reference's
+    ``Models/*.pth`` blobs, which are absent from its tree.  The module creates its parameters in the
+    reference's order with PyTorch's default Conv init, i.e. what ``torch.manual_seed(seed); UNetSmall(8, 4, 96)`` yields."""
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(int(seed))
+        m = UNetSmallB200(in_ch, out_ch, base_ch)
+    return OrderedDict((k, v.detach().clone()) for k, v in m.state_dict().items())
+
+
 class UNetSmallB200(nn.Module):
     def __init__(self, in_ch: int, out_ch: int, base_ch: int = 96, max_batch: int = 16):
         super().__init__()
@@ -65,10 +75,28 @@ class UNetSmallB200(nn.Module):
         self.requires_grad_(False)
         self.max_batch = int(max_batch)
         self._engines = OrderedDict()
+        self._weights_epoch = 0
 
     # ------------------------------------------------------------------ library plumbing
     def _weights_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self._weights_epoch,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def invalidate_weights(self):
+        """Force the next call to repack the parameters into the library.  Needed after writes the autograd version
+        counter does not see -- ``p.data.copy_(...)``, ``p.data.mul_(...)``, EMA swaps through ``.data`` -- which would
+        otherwise leave the engine sampling with the previous fp16 copy.  ``load_state_dict``, ``.to()`` / ``.cuda()`` /
+        ``.float()`` and ordinary in-place parameter updates are detected automatically."""
+        self._weights_epoch += 1
+
+    def load_state_dict(self, *args, **kwargs):
+        res = super().load_state_dict(*args, **kwargs)
+        self.invalidate_weights()
+        return res
+
+    def _apply(self, fn, *args, **kwargs):
+        res = super()._apply(fn, *args, **kwargs)
+        self.invalidate_weights()
+        return res
 
     def engine(self, device: torch.device, H: int, W: int, batch: int) -> "_Engine":
         """Handle for this geometry, (re)created when the batch outgrows it and (re)loaded when parameters change."""
@@ -125,6 +153,18 @@ class UNetSmallB200(nn.Module):
         stream = torch.cuda.current_stream(torch.device(device)).cuda_stream
         _lib.check(_lib.lib().s1s2_debug_loop_layer(eng.h, batch, layer, reps, perf_mode, C.byref(ms), C.c_void_p(stream)), eng.h)
         return float(ms.value)
+
+    def saturation_counts(self, batch: int, device=None):
+        """{activation name: number of fp16 outputs of the LAST model call that sit at the epilogues' saturation value
+        (|v| = 65504) or are not finite} (s1s2_debug_saturation_count; debug aid for trained-scale checkpoints)."""
+        eng = next(reversed(self._engines.values()))
+        L = _lib.lib()
+        n = C.c_int()
+        _lib.check(L.s1s2_debug_saturation_count(eng.h, batch, None, 0, C.byref(n), None), eng.h)
+        counts = (C.c_uint64 * n.value)()
+        stream = torch.cuda.current_stream(torch.device("cuda", eng.key[0])).cuda_stream
+        _lib.check(L.s1s2_debug_saturation_count(eng.h, batch, counts, n.value, C.byref(n), C.c_void_p(stream)), eng.h)
+        return {L.s1s2_view_name(eng.h, i).decode(): int(counts[i]) for i in range(n.value)}
 
     # ------------------------------------------------------------------ the reference's call
     @torch.no_grad()

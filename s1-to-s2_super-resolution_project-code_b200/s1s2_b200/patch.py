@@ -55,8 +55,8 @@ def tile_extract(scene: torch.Tensor, origins, ps: int, vmask: torch.Tensor = No
     mask = torch.empty((N, ps, ps), device=dev, dtype=torch.uint8)
     ratio = torch.empty((N,), device=dev, dtype=torch.float32)
     vm = None
-    if vmask is not None:
-        vm = vmask.to(device=dev, dtype=torch.uint8).contiguous()
+    if vmask is not None:            # any non-zero value counts as valid (a bare uint8 cast would wrap 256 -> 0, -1 -> 255)
+        vm = (vmask.to(dev) != 0).to(torch.uint8).contiguous()
     stream = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(_lib.lib().s1s2_tile_extract(idx, scene.data_ptr(), vm.data_ptr() if vm is not None else None, SH, SW,
                                             org_d.data_ptr(), N, ps, cond.data_ptr(), mask.data_ptr(), ratio.data_ptr(),
@@ -83,7 +83,8 @@ def tile_filter(scene: torch.Tensor, target: torch.Tensor, origins, ps: int, col
     if N and (int(org.min()) < 0 or int(org[:, 0].max()) + ps > SH or int(org[:, 1].max()) + ps > SW):
         raise ValueError("window outside the scene")
     org_d = org.to(dev)
-    cl = colloc.to(device=dev, dtype=torch.uint8).contiguous() if colloc is not None else None
+    # Patch.py:41-49 tests `colloc > 0` on the float raster: 0.5 is valid, -1 is not, 256 does not wrap
+    cl = (colloc.to(dev) > 0).to(torch.uint8).contiguous() if colloc is not None else None
     stats = torch.empty((N, 8), device=dev, dtype=torch.float32)
     th = (C.c_float * 5)(valid_ratio_threshold, variance_threshold, dark_thr, dark_max_ratio, texture_thr)
     stream = torch.cuda.current_stream(dev).cuda_stream
@@ -93,8 +94,19 @@ def tile_filter(scene: torch.Tensor, target: torch.Tensor, origins, ps: int, col
     return stats
 
 
-def stitch(preds: torch.Tensor, origins, ps: int, stride: int, SH: int, SW: int):
-    """preds f32[N,C,ps,ps] (cuda) + origins on the stride grid -> (canvas f32[C,SH,SW], cover u8[SH,SW])."""
+def hann_window(ps: int, device=None) -> torch.Tensor:
+    """Separable blend window f32[ps]: w[i] = 0.5 - 0.5 cos(2 pi (i + 0.5) / ps) -- the Hann window sampled at pixel
+    centres, strictly positive, so every covered pixel keeps a non-zero weight sum."""
+    i = torch.arange(ps, dtype=torch.float64)
+    w = (0.5 - 0.5 * torch.cos(2.0 * torch.pi * (i + 0.5) / ps)).to(torch.float32)
+    return w.to(device) if device is not None else w
+
+
+def stitch(preds: torch.Tensor, origins, ps: int, stride: int, SH: int, SW: int, window=None):
+    """preds f32[N,C,ps,ps] (cuda) + origins on the stride grid -> (canvas f32[C,SH,SW], cover u8[SH,SW]).
+
+    window: None = uniform weights (the primary, bit-reproducible definition), "hann" or a f32[ps] tensor = separable
+    per-pixel weights w[ly] * w[lx] (SURVEY.md section 8 a9's optional variant)."""
     dev = preds.device
     idx = _dev_index(preds)
     preds = preds.to(torch.float32).contiguous()
@@ -108,10 +120,17 @@ def stitch(preds: torch.Tensor, origins, ps: int, stride: int, SH: int, SW: int)
         key = org[:, 0].astype(np.int64) * (SW + 1) + org[:, 1]
         if (np.diff(key) <= 0).any():
             raise ValueError("origins must be strictly ascending in (row, col) order (Patch.py iteration order)")
+    win = None
+    if window is not None:
+        win = hann_window(ps, dev) if isinstance(window, str) and window == "hann" else window
+        if not isinstance(win, torch.Tensor) or win.numel() != ps:
+            raise ValueError("window must be None, 'hann' or a tensor of ps weights")
+        win = win.to(device=dev, dtype=torch.float32).contiguous()
     org_d = torch.as_tensor(org).to(dev)
     canvas = torch.empty((Cn, SH, SW), device=dev, dtype=torch.float32)
     cover = torch.empty((SH, SW), device=dev, dtype=torch.uint8)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(_lib.lib().s1s2_stitch(idx, preds.data_ptr(), org_d.data_ptr(), N, Cn, ps, stride, SH, SW, canvas.data_ptr(),
-                                      cover.data_ptr(), C.c_void_p(stream)))
+    _lib.check(_lib.lib().s1s2_stitch_weighted(idx, preds.data_ptr(), org_d.data_ptr(), N, Cn, ps, stride, SH, SW,
+                                               win.data_ptr() if win is not None else None, canvas.data_ptr(),
+                                               cover.data_ptr(), C.c_void_p(stream)))
     return canvas, cover

@@ -72,24 +72,34 @@ def run_steps(model: UNetSmallB200, steps, cond, x_init, init_scale=1.0, step_no
     return (out, taps) if taps else out
 
 
-def run_steps_host(model: UNetSmallB200, steps, cond_host, x_init_host, init_scale=1.0, device=None):
-    """End-to-end entry with HOST tensors (pinned recommended): H2D, sample, D2H, synchronise (s1s2_sample_host)."""
+def host_result_buffer(model: UNetSmallB200, shape):
+    """The pinned host tensor run_steps_host returns results of this shape in (allocated on first use, then reused)."""
+    key = ("host_out", tuple(shape))
+    cache = model.__dict__.setdefault("_host_buffers", {})
+    out = cache.get(key)
+    if out is None:
+        out = cache[key] = torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True)
+    return out
+
+
+def run_steps_host(model: UNetSmallB200, steps, cond_host, x_init_host, init_scale=1.0, device=None, batch=None):
+    """End-to-end entry with HOST tensors (pinned recommended): N patches in batches of `batch` (default: all at once, at
+    most the model's max_batch) through s1s2_sample_host_stream -- upload of batch i+1 and download of batch i-1 overlap the
+    model calls of batch i; returns a pinned host tensor (reused across calls) once everything has drained."""
     dev = torch.device(device if device is not None else "cuda")
-    B, _, H, W = cond_host.shape
-    eng = model.engine(dev, H, W, B)
+    N, _, H, W = cond_host.shape
+    if batch is None:
+        batch = min(N, max(model.max_batch, 1))
+    eng = model.engine(dev, H, W, batch)
     assert cond_host.device.type == "cpu" and x_init_host.device.type == "cpu"
     cond_host = cond_host.to(torch.float32).contiguous()
     x_init_host = x_init_host.to(torch.float32).contiguous()
-    key = ("host_out", tuple(x_init_host.shape))
-    cache = model.__dict__.setdefault("_host_buffers", {})
-    out = cache.get(key)
-    if out is None:          # pinned result buffer, reused across calls (the caller copies out of it if it keeps it)
-        out = cache[key] = torch.empty(x_init_host.shape, dtype=torch.float32, pin_memory=True)
+    out = host_result_buffer(model, x_init_host.shape)     # reused across calls (the caller copies out of it if it keeps it)
     n = len(steps)
     arr = (_lib.Step * n)(*steps)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(_lib.lib().s1s2_sample_host(eng.h, arr, n, _ptr(cond_host), _ptr(x_init_host), float(init_scale),
-                                           _ptr(out), B, C.c_void_p(stream)), eng.h)
+    _lib.check(_lib.lib().s1s2_sample_host_stream(eng.h, arr, n, _ptr(cond_host), _ptr(x_init_host), float(init_scale),
+                                                  _ptr(out), N, int(batch), C.c_void_p(stream)), eng.h)
     return out
 
 
@@ -114,16 +124,21 @@ def ddim_multistep_eval(model, x_gt, x_cond, alpha_bar, mask, t_start=200, steps
     return masked_mae(x0, x_gt, mask), masked_mse(x0, x_gt, mask), x0
 
 
+def _one_step_noise(x_gt, rng_seed, noise):
+    """The reference's draw: ``if rng_seed is not None: torch.manual_seed(rng_seed)`` then ``torch.randn_like(x_gt)``
+    (DDIM_Multi-step.py:157,162) -- the global generator is re-seeded, exactly as the scripts do."""
+    if noise is not None:
+        return noise
+    if rng_seed is not None:
+        torch.manual_seed(int(rng_seed))
+    return torch.randn_like(x_gt)
+
+
 @torch.no_grad()
 def one_step_recon(model, x_gt, x_cond, alpha_bar, mask, t_small, rng_seed=None, noise=None):
     T = len(alpha_bar)
     t = max(1, min(int(t_small), T - 1))
-    if noise is None:
-        if rng_seed is not None:
-            g = torch.Generator(device=x_gt.device).manual_seed(int(rng_seed))
-            noise = torch.randn(x_gt.shape, device=x_gt.device, generator=g)
-        else:
-            noise = torch.randn_like(x_gt)
+    noise = _one_step_noise(x_gt, rng_seed, noise)
     a = alpha_bar[t].to(x_gt.device).view(-1, 1, 1, 1)
     x_t = torch.sqrt(a) * x_gt + torch.sqrt(1 - a) * noise
     ab = schedule._abar_cpu(alpha_bar)
@@ -148,15 +163,12 @@ def ddim_multistep_eval_v(model, x_gt, x_cond, alpha_bar, mask, t_start=200, ste
 
 
 @torch.no_grad()
-def one_step_recon_v(model, x_gt, x_cond, alpha_bar, mask, t_small, rng_seed=None, noise=None):
+def one_step_recon_v(model, x_gt, x_cond, alpha_bar, mask, t_small, rng_seed=None, noise=None, allow_t0=False):
+    """DDIM_Multi-step_v_Prediction.py:211-227: t_small is clamped to [1, T-1] like the reference.  ``allow_t0=True`` (not
+    in the reference's signature) lets the t = 0 identity check of Onestep_v_Prediction.py:184-197 run through here."""
     T = len(alpha_bar)
-    t = max(0, min(int(t_small), T - 1))
-    if noise is None:
-        if rng_seed is not None:
-            g = torch.Generator(device=x_gt.device).manual_seed(int(rng_seed))
-            noise = torch.randn(x_gt.shape, device=x_gt.device, generator=g)
-        else:
-            noise = torch.randn_like(x_gt)
+    t = max(0 if allow_t0 else 1, min(int(t_small), T - 1))
+    noise = _one_step_noise(x_gt, rng_seed, noise)
     a = alpha_bar[t].to(x_gt.device).view(-1, 1, 1, 1)
     x_t = torch.sqrt(a) * x_gt + torch.sqrt(1 - a) * noise
     ab = schedule._abar_cpu(alpha_bar)

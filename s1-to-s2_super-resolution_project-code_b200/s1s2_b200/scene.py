@@ -8,20 +8,43 @@ scene rasters on the device.  Patches are independent units (SURVEY.md section 8
 gather of the predicted patches (f32[n_r,4,ps,ps]) to rank 0, which stitches.  The result does not depend on the
 world size: the initial noise of a patch is keyed by its global index and every kernel is batch-independent.
 """
+import ctypes as C
+
 import numpy as np
 import torch
 
-from . import patch, samplers
+from . import _lib, patch, samplers
 
 
-def patch_noise(indices, shape, seed_base, device):
-    """Unit-normal initial noise f32[len(indices), *shape], one generator per patch seeded seed_base + global index
-    (the per-file seeding of Evaluation/DDIM_Sweep.py:193,404)."""
-    out = torch.empty((len(indices),) + tuple(shape), device=device, dtype=torch.float32)
-    g = torch.Generator(device=device)
-    for k, idx in enumerate(indices):
-        g.manual_seed(int(seed_base) + int(idx))
-        out[k] = torch.randn(shape, generator=g, device=device, dtype=torch.float32)
+def patch_noise(indices, shape, seed_base, device, method="philox"):
+    """Unit-normal initial noise f32[len(indices), *shape] keyed by GLOBAL patch index, so the draw of a patch does not
+    depend on the rank or batch slot it lands in.
+
+    method "philox" (default): one library kernel for all patches (s1s2_patch_noise: Philox4x32-10 keyed by seed_base,
+    counter = (element, patch index)).  method "torch": one torch generator per patch seeded seed_base + index -- the
+    per-file seeding of Evaluation/DDIM_Sweep.py:193,404, bit-identical to what that script would draw on this device
+    (one generator re-seed + one launch per patch: fine for a file list, slow for the 3 249 windows of a stride-32 scene)."""
+    n = len(indices)
+    out = torch.empty((n,) + tuple(shape), device=device, dtype=torch.float32)
+    if n == 0:
+        return out
+    if method == "torch":
+        g = torch.Generator(device=device)
+        for k, idx in enumerate(indices):
+            g.manual_seed(int(seed_base) + int(idx))
+            out[k] = torch.randn(shape, generator=g, device=device, dtype=torch.float32)
+        return out
+    if method != "philox":
+        raise ValueError(f"unknown noise method '{method}'")
+    dev = torch.device(device)
+    didx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ids = torch.as_tensor(np.asarray(indices, dtype=np.int64)).to(dev)
+    elems = int(np.prod(shape))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for lo in range(0, n, 65535):
+        m = min(65535, n - lo)
+        _lib.check(_lib.lib().s1s2_patch_noise(didx, C.c_uint64(int(seed_base) & (2 ** 64 - 1)), C.c_void_p(ids[lo:].data_ptr()), m,
+                                               elems, C.c_void_p(out[lo:].data_ptr()), C.c_void_p(stream)))
     return out
 
 
@@ -58,28 +81,56 @@ def gather_to_rank0(local: torch.Tensor, counts, rank: int, world: int, group=No
     return torch.cat([bufs[r][:counts[r]] for r in range(world)], 0)
 
 
+class _PhaseClock:
+    """CUDA-event stopwatch over the phases of one generate_scene call (no host synchronisation until read)."""
+
+    def __init__(self, enabled):
+        self.enabled = enabled
+        self.marks = []
+
+    def mark(self, name):
+        if self.enabled:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def read(self, into):
+        if not self.enabled or not self.marks:
+            return
+        torch.cuda.synchronize()
+        for (_, e0), (name, e1) in zip(self.marks[:-1], self.marks[1:]):
+            into[name + "_ms"] = into.get(name + "_ms", 0.0) + e0.elapsed_time(e1)
+
+
 def generate_scene(model, scene, alpha_bar, ps=256, stride=64, param="v", steps=50, t_start=999, batch=64,
                    seed_base=1234, vmask=None, valid_ratio_threshold=0.0, rank=0, world=1, group=None,
-                   extract_fn=None, sample_fn=None, stitch_fn=None, noise_fn=None):
+                   extract_fn=None, sample_fn=None, stitch_fn=None, noise_fn=None, window=None, timings=None):
     """scene f32[4,SH,SW] on this rank's device (HH dB, HV dB, incidence deg, elevation m; NaN = no data).
 
     Returns on rank 0 a dict(canvas f32[C,SH,SW], cover u8[SH,SW], origins i32[N,2], kept bool[N], preds f32[Nk,C,ps,ps]);
     None on the other ranks.  The *_fn hooks exist for the CPU tests of the sharding logic (gloo, no GPU): the
-    product path uses the CUDA kernels and has no fallback."""
+    product path uses the CUDA kernels and has no fallback.  `window`: None = uniform overlap blend, "hann" = Hann-weighted
+    (patch.stitch).  `timings` (dict, CUDA only): receives extract_ms / noise_ms / sample_ms / gather_ms / stitch_ms of this
+    rank, measured with CUDA events on the current stream."""
     extract_fn = extract_fn or patch.tile_extract
     sample_fn = sample_fn or sample_patches
     stitch_fn = stitch_fn or patch.stitch
     noise_fn = noise_fn or patch_noise
+    clock = _PhaseClock(timings is not None and scene.device.type == "cuda")
     SH, SW = int(scene.shape[1]), int(scene.shape[2])
     origins = patch.tile_origins(SH, SW, ps, stride)
     N = len(origins)
     lo, hi = patch.shard_range(N, rank, world)
+    clock.mark("start")
     cond, mask, ratio = extract_fn(scene, origins[lo:hi], ps, vmask)
     keep = ratio >= valid_ratio_threshold if (hi - lo) else torch.zeros((0,), dtype=torch.bool, device=scene.device)
     kept_idx = (torch.nonzero(keep).flatten().cpu().numpy() + lo).astype(np.int64)      # global patch indices
+    clock.mark("extract")
     C_tgt = model.outc.out_channels
     noise = noise_fn(kept_idx, (C_tgt, ps, ps), seed_base, scene.device)
+    clock.mark("noise")
     preds = sample_fn(model, cond[keep], alpha_bar, noise, param=param, steps=steps, t_start=t_start, batch=batch)
+    clock.mark("sample")
 
     # which patches every rank kept (tiny, host-side): ranks agree on counts before the fixed-size gather
     if world > 1:
@@ -92,10 +143,36 @@ def generate_scene(model, scene, alpha_bar, ps=256, stride=64, param="v", steps=
         kept_all = keep.cpu().numpy().astype(bool)
     counts = [int(kept_all[slice(*patch.shard_range(N, r, world))].sum()) for r in range(world)]
     allp = gather_to_rank0(preds, counts, rank, world, group)
+    clock.mark("gather")
     if rank != 0:
+        clock.read(timings)
         return None
-    canvas, cover = stitch_fn(allp, origins[kept_all], ps, stride, SH, SW)
+    if window is None:
+        canvas, cover = stitch_fn(allp, origins[kept_all], ps, stride, SH, SW)
+    else:
+        canvas, cover = stitch_fn(allp, origins[kept_all], ps, stride, SH, SW, window=window)
+    clock.mark("stitch")
+    clock.read(timings)
     return dict(canvas=canvas, cover=cover, origins=origins, kept=kept_all, preds=allp)
+
+
+def generate_scene_host(model, scene_host, alpha_bar, device, rank=0, world=1, **kw):
+    """generate_scene for a scene raster held in HOST memory (pinned recommended), the way a caller that has just read the
+    rasters from disk holds it (Patch.py:152-187): uploads the scene to `device`, runs generate_scene there, and on rank 0
+    downloads canvas and cover into pinned host tensors.  Returns (result dict with host `canvas` / `cover`, bytes up,
+    bytes down); the other ranks get (None, bytes up, 0)."""
+    scene_d = scene_host.to(device, non_blocking=True)
+    res = generate_scene(model, scene_d, alpha_bar, rank=rank, world=world, **kw)
+    up = scene_host.numel() * scene_host.element_size()
+    if res is None:
+        return None, up, 0
+    canvas = torch.empty(res["canvas"].shape, dtype=torch.float32, pin_memory=True)
+    cover = torch.empty(res["cover"].shape, dtype=torch.uint8, pin_memory=True)
+    canvas.copy_(res["canvas"], non_blocking=True)
+    cover.copy_(res["cover"], non_blocking=True)
+    torch.cuda.current_stream(device).synchronize()
+    res = dict(res, canvas=canvas, cover=cover)
+    return res, up, canvas.numel() * 4 + cover.numel()
 
 
 def synthetic_scene(SH=2048, SW=2048, seed=0, nan_fraction=0.02):

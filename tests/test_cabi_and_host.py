@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
     L = lib.lib()
     for name in declared:
         assert getattr(L, name) is not None
-    assert L.s1s2_abi_version() == 2
+    assert L.s1s2_abi_version() == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

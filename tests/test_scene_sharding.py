@@ -42,6 +42,12 @@ def _sample(model, cond, alpha_bar, noise, param="v", steps=50, t_start=999, bat
     return torch.clamp(cond * 0.5 + noise * 0.25 + float(alpha_bar[3]), 0.0, 1.0)
 
 
+def _noise(indices, shape, seed_base, device):
+    # per-patch torch generator keyed by the global index (the product default is the library's Philox kernel: CUDA only)
+    from s1s2_b200 import scene as sc
+    return sc.patch_noise(indices, shape, seed_base, device, method="torch")
+
+
 def _stitch(preds, origins, ps, stride, SH, SW):
     from oracle import patch as opatch
     c, m = opatch.stitch(preds.numpy(), np.asarray(origins), SH, SW)
@@ -60,7 +66,7 @@ def _run(rank, world, port, out_path, thr):
     scene = sc.synthetic_scene(96, 160, seed=3, nan_fraction=0.05)
     scene[:, :40, :48] = float("nan")                       # a few windows fall under the valid-ratio threshold
     res = sc.generate_scene(_FakeModel(), scene, abar, ps=32, stride=16, batch=3, valid_ratio_threshold=thr, rank=rank,
-                            world=world, extract_fn=_extract, sample_fn=_sample, stitch_fn=_stitch)
+                            world=world, extract_fn=_extract, sample_fn=_sample, stitch_fn=_stitch, noise_fn=_noise)
     if rank == 0:
         torch.save({k: (v if isinstance(v, torch.Tensor) else torch.as_tensor(v)) for k, v in res.items()}, out_path)
     else:

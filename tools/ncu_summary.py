@@ -8,6 +8,7 @@ usage: python tools/ncu_summary.py REPORT.ncu-rep OUT.txt [--layers] [--traffic 
 import csv
 import io
 import json
+import os
 import subprocess
 import sys
 
@@ -69,7 +70,11 @@ def main():
     if traffic and layers:
         rd = sum(v["dram_read_GB"] for v in tj["layers"].values())
         wr = sum(v["dram_write_GB"] for v in tj["layers"].values())
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
         res = {"source": f"{out} (ncu --set full, one model call = 16 launches, batch 64)", "per": "model call of 64 patches",
+               "csrc_fingerprint": bench.csrc_fingerprint(),     # bench.py quotes this capture only while the kernels are unchanged
+               "git_head": os.environ.get("S1S2_GIT_HEAD"),
                "dram_read_GB": round(rd, 6), "dram_write_GB": round(wr, 6), "dram_total_GB": round(rd + wr, 6),
                "algorithmic_activation_GB": 18.624, "layers": tj["layers"]}
         json.dump(res, open(traffic, "w"), indent=1)
