@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
             acc_ph ^= 1;                            // this group's accumulator is used once per two tiles
         }
         if constexpr (MODE == MODE_STORE) {
-            if (issuer) bulk_wait0();
+            if (issuer) bulk_wait_read0();       // see conv_umma_kernel: writes are ordered by grid completion
         }
     }
 

@@ -717,7 +717,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     }
 
     if constexpr (kTmaStore) {
-        if (warp == 4 && lane == 0) bulk_wait0();   // all output stores of this CTA have completed
+        // the staging buffers may be released once the outstanding stores have READ them; completion of the writes is
+        // ordered by grid completion (what the next kernel's griddepcontrol.wait / stream order waits for)
+        if (warp == 4 && lane == 0) bulk_wait_read0();
     }
     tc_fence_before();
     __syncthreads();

@@ -833,9 +833,24 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     }
     if (getenv("S1S2_NO_PX") == nullptr) {       // default: pixels-on-N kernels for the Cout = 96 full-resolution layers
         for (Layer& L : h->layers) {
-            if (L.kid == K_N96) L.kid = getenv("S1S2_C10_UMMA") != nullptr ? K_HSTORE96 : K_PX_STORE;     // A/B: Cout on N, halo, TPS 3
-            if (L.kid == K_HEAD) L.kid = getenv("S1S2_C12_UMMA") != nullptr ? K_HHEAD96 : K_PX_HEAD32;    // A/B: same, TPS 9
+            // conv1.0: Cout on N with 96-column tiles, three taps per stage (measured 8 % faster than the pixels-on-N kernel,
+            // whose M = 128 MMAs carry 96 real rows; S1S2_C10_PX=1 restores that one for A/B).  conv1.2 + head: pixels on N
+            // (the Cout-on-N head, S1S2_C12_UMMA=1, is 20 % slower: one epilogue warpgroup does the 96 x 4 head FMAs per pixel).
+            if (L.kid == K_N96) L.kid = getenv("S1S2_C10_PX") != nullptr ? K_PX_STORE : K_HSTORE96;
+            if (L.kid == K_HEAD) L.kid = getenv("S1S2_C12_UMMA") != nullptr ? K_HHEAD96 : K_PX_HEAD32;
         }
+    }
+    if (const char* force = getenv("S1S2_FORCE")) {        // measurement aid: "layer=KERNEL[,layer=KERNEL...]", e.g. conv2.2=HC96IN
+        static const struct { const char* name; KernelId kid; } names[] = {
+            {"HSTORE", K_HSTORE}, {"HPOOL", K_HPOOL}, {"HSTORE256", K_HSTORE256}, {"HPOOL256", K_HPOOL256}, {"HC96IN", K_HC96IN},
+            {"HSTORE96", K_HSTORE96}, {"HPOOL96", K_HPOOL96}, {"PX_STORE", K_PX_STORE}, {"STORE", K_STORE}, {"N96", K_N96}};
+        std::string spec = force;
+        for (Layer& L : h->layers)
+            for (const auto& nm : names) {
+                const std::string key = std::string(L.name) + "=" + nm.name;
+                const size_t at = spec.find(key);
+                if (at != std::string::npos && (at + key.size() == spec.size() || spec[at + key.size()] == ',')) L.kid = nm.kid;
+            }
     }
     if (getenv("S1S2_NO_ALTS") == nullptr) {     // narrower tilings for small batches (pick_variant), widest first
         for (Layer& L : h->layers) {

@@ -115,6 +115,7 @@ class UNetSmallB200(nn.Module):
         if eng is None:
             eng = _Engine(idx, H, W, max(batch, self.max_batch))
             self._engines[key] = eng
+        self._engines.move_to_end(key)           # activation() / saturation_counts() read the engine used last
         ver = self._weights_version()
         if eng.weights_version != ver:
             sd = self.state_dict()

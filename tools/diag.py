@@ -78,7 +78,33 @@ def loop_mode():
                   f"util@clk {util:5.3f}  power {clk.get('power_w_max')} reasons {clk.get('reasons')}", flush=True)
 
 
+def overhead_mode():
+    """python tools/diag.py overhead : per-model-call time of the fused chain at batch 1 for shrinking patch sizes -- at 16 x 16
+    the arithmetic is negligible, so the time per call / 16 is the fixed cost of one launch in the chain (prologue, first
+    loads, tail, hand-over to the next kernel)."""
+    sd, m = make(1)
+    _, _, ab = osched.make_schedule(1000)
+    steps = schedule.steps_grid_b(ab, schedule.grid_b(999, 50), "v")
+    for hw in (16, 32, 64, 128, 256):
+        cond = torch.randn((1, 4, hw, hw), device="cuda")
+        x = torch.randn((1, 4, hw, hw), device="cuda")
+        for _ in range(3):
+            samplers.run_steps(m, steps, cond, x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            samplers.run_steps(m, steps, cond, x)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 10 / len(steps) * 1e3
+        print(f"{hw:3d} x {hw:3d}, batch 1: {us:7.1f} us per model call = {us / 16:5.2f} us per launch", flush=True)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "overhead":
+        overhead_mode()
+        sys.exit(0)
     if sys.argv[1] == "loop":
         loop_mode()
         sys.exit(0)
