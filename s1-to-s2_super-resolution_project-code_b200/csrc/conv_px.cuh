@@ -269,7 +269,12 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
             const int ty = (tile / tiles_x) % tiles_y;
             const int n = tile / (tiles_x * tiles_y);
             float s_up = 1.f, s_dn = 1.f;
-            if (p.amax_in != nullptr) s_dn = range_scale(__ldg(p.amax_in + n), s_up);
+            [[maybe_unused]] bool poisoned = false;      // invalid call for this patch (pack_input_kernel): the head writes NaN
+            if (p.amax_in != nullptr) {
+                const uint32_t bits = __ldg(p.amax_in + n);
+                s_dn = range_scale(bits, s_up);
+                poisoned = bits > 0x7F800000u;
+            }
 
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
@@ -366,7 +371,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < kHeadOut; ++k) {
                         const size_t idx = (static_cast<size_t>(n) * kHeadOut + k) * plane + pix;
-                        const float pr = o[k] * s_up;
+                        const float pr = poisoned ? __uint_as_float(kAmaxPoison) : o[k] * s_up;
                         if (p.head.pred_out != nullptr) p.head.pred_out[idx] = pr;
                         res[k] = pr;
                         if (sc.kind != STEP_NONE) {

@@ -42,6 +42,9 @@ enum : int { STEP_FLAG_FINAL = 1, STEP_FLAG_NOISE = 2, STEP_FLAG_PHILOX = 4 };
 enum : int { LAYER_FLAG_FIRST = 1 };   // first layer: apply the range scale in the epilogue (inputs are unscaled)
 
 constexpr float kXSplit = 4096.f;      // x_t travels as an fp16 pair: x = kXSplit * hi + lo
+constexpr uint32_t kAmaxPoison = 0x7FC00000u;   // amax word of a patch whose call is invalid (timestep outside the fp16-exact
+                                                // range): above every finite float's bits, so atomicMax keeps it; the head
+                                                // then writes NaN for that patch
 
 // One scheduler update; travels by value in the kernel parameters, so a sampling loop is enqueued (or captured in
 // a CUDA graph) without device-side bookkeeping or host round trips.
@@ -540,7 +543,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             const int n = (tn << (7 - p.tw_log2 - p.th_log2)) + ln;
             const bool live = (n < p.B) && (y < p.H) && (x < p.W);
             float s_up = 1.f, s_dn = 1.f;
-            if (live && p.amax_in != nullptr) s_dn = range_scale(__ldg(p.amax_in + n), s_up);
+            [[maybe_unused]] bool poisoned = false;
+            if (live && p.amax_in != nullptr) {
+                const uint32_t bits = __ldg(p.amax_in + n);
+                s_dn = range_scale(bits, s_up);
+                poisoned = bits > 0x7F800000u;
+            }
 
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
@@ -578,7 +586,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
                     for (int k = 0; k < kHeadOut; ++k) {
                         const size_t idx = (static_cast<size_t>(n) * kHeadOut + k) * plane + pix;
-                        const float pr = o[k] * s_up;
+                        const float pr = poisoned ? __uint_as_float(kAmaxPoison) : o[k] * s_up;
                         if (p.head.pred_out != nullptr) p.head.pred_out[idx] = pr;
                         res[k] = pr;
                         if (sc.kind != STEP_NONE) {

@@ -68,8 +68,9 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
         const int pix = static_cast<int>(i - static_cast<size_t>(b) * HW);
         float t = t_const;
         if (t_idx != nullptr) {         // outside the fp16-exact integer range the time planes would be silently rounded:
-            const int64_t ti = t_idx[b];                    // poison the call instead (NaN planes -> NaN output)
-            t = (ti >= 0 && ti <= 2048) ? static_cast<float>(ti) : __int_as_float(0x7FC00000);
+            const int64_t ti = t_idx[b];                    // poison the patch instead -- a NaN amax makes the head write NaN
+            if (ti >= 0 && ti <= 2048) t = static_cast<float>(ti);
+            else { t = 0.f; mx = __uint_as_float(kAmaxPoison); }
         }
         float xv[4], cv[4], hi[4], lo[4];
 #pragma unroll
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
             cv[k] = cond[b * c_bstride + static_cast<size_t>(k) * HW + pix];
             if (state != nullptr) state[(static_cast<size_t>(b) * 4 + k) * HW + pix] = xv[k];
             split_x(xv[k], hi[k], lo[k]);
-            mx = fmaxf(mx, fabsf(xv[k]));
+            if (__float_as_uint(mx) != kAmaxPoison) mx = fmaxf(mx, fabsf(xv[k]));
         }
         uint4 lo4, hi4;
         lo4.x = pack_half2_sat(lo[0], lo[1]);

@@ -1,6 +1,6 @@
 """Summarise an `ncu --set full` report into the per-launch table kept under profiles/ (run where ncu is installed).
 
-usage: python tools/ncu_summary.py REPORT.ncu-rep OUT.txt [--layers] [--traffic profiles/traffic.json] [--title "..."]
+usage: python tools/ncu_summary.py REPORT.ncu-rep OUT.txt [--layers] [--batch B] [--traffic profiles/traffic.json] [--title "..."]
 
 --layers   the report holds one model call (16 conv launches, in execution order): label rows with the layer names and
            add the sum line; with --traffic also writes the DRAM-traffic table bench.py reads for roofline.traffic.
@@ -34,6 +34,7 @@ def main():
     layers = "--layers" in sys.argv
     traffic = sys.argv[sys.argv.index("--traffic") + 1] if "--traffic" in sys.argv else None
     title = sys.argv[sys.argv.index("--title") + 1] if "--title" in sys.argv else rep
+    batch = int(sys.argv[sys.argv.index("--batch") + 1]) if "--batch" in sys.argv else 64
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, body = rows[0], rows[1], rows[2:]
@@ -63,8 +64,8 @@ def main():
         if layers and n < len(LAYERS):
             tj["layers"][LAYERS[n]] = {"dram_read_GB": round(by["dram_rd_GB"], 6), "dram_write_GB": round(by["dram_wr_GB"], 6)}
     if layers:
-        lines.append(f"# sum of the {len(body)} launches: {tot_ms:.3f} ms for 64 patches x 301.85 GFLOP = "
-                     f"{64 * 301.851 / tot_ms:.0f} TFLOP/s (cold, serialised under the profiler)")
+        lines.append(f"# sum of the {len(body)} launches: {tot_ms:.3f} ms for {batch} patch(es) x 301.85 GFLOP = "
+                     f"{batch * 301.851 / tot_ms:.0f} TFLOP/s (cold, serialised under the profiler)")
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
     if traffic and layers:
