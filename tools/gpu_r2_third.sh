@@ -18,5 +18,6 @@ python tools/ncu_summary.py $O/prof_b1_$T.ncu-rep $O/ncu_full_per_layer_b1_$T.tx
     --title "ncu --set full --clock-control none -k regex:conv_ -s 32 -c 16 python tools/diag.py time 1 2 (one model call, B=1, 256x256; serialised, cold)" > /dev/null
 ncu -i $O/prof_b1_$T.ncu-rep --page raw --csv > $O/prof_b1_${T}_raw.csv 2>/dev/null
 ncu -i $O/prof_b64_$T.ncu-rep --page raw --csv > $O/prof_b64_${T}_raw.csv 2>/dev/null
+rm -f $O/prof_b64_$T.ncu-rep            # gpurun brings back at most 64 MiB: keep the batch-1 report only
 python tools/hbm_kernels.py $O/hbm_kernels_$T.json > $O/hbm_kernels_$T.log 2>&1; echo "hbm rc=$?"
 ls -la $O | tail -20; du -sh $O
