@@ -383,6 +383,9 @@ def scene_block(model, abar, dev, rank, world, batch):
     import torch.distributed as dist
     from s1s2_b200 import scene as sc
     scn = sc.synthetic_scene(2048, 2048, seed=0).pin_memory()
+    if world > 1:                                  # communicator set-up (first gather) stays outside the timed scenes
+        sc.gather_to_rank0(torch.zeros((1, 4, 8, 8), device=dev), [1] * world, rank, world)
+        torch.cuda.synchronize()
     out = []
     for stride in (64, 32):
         tm = {}
@@ -397,7 +400,7 @@ def scene_block(model, abar, dev, rank, world, batch):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        keys = ("extract_ms", "noise_ms", "sample_ms", "gather_ms", "stitch_ms")
+        keys = ("extract_ms", "noise_ms", "sample_ms", "sync_ms", "gather_ms", "stitch_ms")
         vec = torch.tensor([ms] + [tm.get(k, 0.0) for k in keys], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(vec, op=dist.ReduceOp.MAX)

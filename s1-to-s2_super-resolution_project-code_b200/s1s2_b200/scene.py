@@ -110,8 +110,8 @@ def generate_scene(model, scene, alpha_bar, ps=256, stride=64, param="v", steps=
     Returns on rank 0 a dict(canvas f32[C,SH,SW], cover u8[SH,SW], origins i32[N,2], kept bool[N], preds f32[Nk,C,ps,ps]);
     None on the other ranks.  The *_fn hooks exist for the CPU tests of the sharding logic (gloo, no GPU): the
     product path uses the CUDA kernels and has no fallback.  `window`: None = uniform overlap blend, "hann" = Hann-weighted
-    (patch.stitch).  `timings` (dict, CUDA only): receives extract_ms / noise_ms / sample_ms / gather_ms / stitch_ms of this
-    rank, measured with CUDA events on the current stream."""
+    (patch.stitch).  `timings` (dict, CUDA only): receives extract_ms / noise_ms / sample_ms / sync_ms / gather_ms / stitch_ms of
+    this rank (sync = waiting for the slowest rank at the keep-flag all-reduce; gather = the transfer itself), measured with CUDA events on the current stream."""
     extract_fn = extract_fn or patch.tile_extract
     sample_fn = sample_fn or sample_patches
     stitch_fn = stitch_fn or patch.stitch
@@ -141,6 +141,7 @@ def generate_scene(model, scene, alpha_bar, ps=256, stride=64, param="v", steps=
         kept_all = flags.bool().cpu().numpy()
     else:
         kept_all = keep.cpu().numpy().astype(bool)
+    clock.mark("sync")                  # (world > 1: the all-reduce is where a fast rank waits for the slowest one)
     counts = [int(kept_all[slice(*patch.shard_range(N, r, world))].sum()) for r in range(world)]
     allp = gather_to_rank0(preds, counts, rank, world, group)
     clock.mark("gather")
