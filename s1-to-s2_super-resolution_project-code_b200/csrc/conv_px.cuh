@@ -83,7 +83,6 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
     const int tiles_x = p.W >> 3, tiles_y = (p.H + 31) >> 5;
     const int num_tiles = tiles_x * tiles_y * p.B;
 
-    pdl_launch_dependents();                    // see conv_umma_kernel: the next kernel may be scheduled from now on
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmap_a);
         tma_prefetch_desc(&p.tmap_b);
@@ -105,12 +104,13 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
+    if (threadIdx.x < 128) sbias[threadIdx.x] = threadIdx.x < p.cout ? p.bias[threadIdx.x] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // As in conv_umma_kernel every role waits on the previous kernel for itself (griddepcontrol.wait): the producer after
-    // requesting the first weight tiles, the epilogue groups after staging the bias; the MMA warp never touches global memory.
+    pdl_launch_dependents();                    // see conv_umma_kernel: the prologue above overlaps the previous kernel's tail
+    pdl_wait();
 
     if (warp == 0) {
         // ================================================================= TMA producer
@@ -137,22 +137,6 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
         };
         int tile = blockIdx.x, chunk = 0;
         auto advance = [&](int& t, int& c) { if (++c == p.chunks) { c = 0; t += gridDim.x; } };
-        auto load_weights = [&](int kcol) {          // one ring stage: TPS weight tiles of one channel chunk
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(&full_bar[s], L::kStage);
-#pragma unroll
-                for (int j = 0; j < TPS; ++j)
-                    tma_load_2d(stage_base + s * L::kStage + j * L::kABox, &p.tmap_b, &full_bar[s], kcol + j * p.tap_kstride, 0);
-            }
-            __syncwarp();
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-        };
-        // weight tiles of the first (tile, chunk) position go out before the wait on the previous kernel
-        int pre_st = 0;
-        if (tile < num_tiles)
-            for (; pre_st < kStagesPerChunk && pre_st < STAGES; ++pre_st) load_weights(pre_st * TPS * p.tap_kstride);
-        pdl_wait();
         if constexpr (HSLOTS >= 3) {
             // the halo cursor runs HSLOTS - 2 positions ahead of the weight stream (its slot was freed two positions earlier)
             constexpr int kAhead = HSLOTS - 2;
@@ -161,8 +145,18 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
                 if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
             while (tile < num_tiles) {
                 if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
-                for (int st = pre_st; st < kStagesPerChunk; ++st) load_weights(chunk * KBOX + st * TPS * p.tap_kstride);
-                pre_st = 0;
+                int kcol = chunk * KBOX;
+                for (int st = 0; st < kStagesPerChunk; ++st, kcol += TPS * p.tap_kstride) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[s], L::kStage);
+#pragma unroll
+                        for (int j = 0; j < TPS; ++j)
+                            tma_load_2d(stage_base + s * L::kStage + j * L::kABox, &p.tmap_b, &full_bar[s], kcol + j * p.tap_kstride, 0);
+                    }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
                 advance(tile, chunk);
             }
         } else {
@@ -170,11 +164,19 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
             while (tile < num_tiles) {
                 int ntile = tile, nchunk = chunk;
                 advance(ntile, nchunk);
-                for (int st = 0; st < kStagesPerChunk; ++st) {
-                    if (st >= pre_st) load_weights(chunk * KBOX + st * TPS * p.tap_kstride);
+                int kcol = chunk * KBOX;
+                for (int st = 0; st < kStagesPerChunk; ++st, kcol += TPS * p.tap_kstride) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[s], L::kStage);
+#pragma unroll
+                        for (int j = 0; j < TPS; ++j)
+                            tma_load_2d(stage_base + s * L::kStage + j * L::kABox, &p.tmap_b, &full_bar[s], kcol + j * p.tap_kstride, 0);
+                    }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                     if (st == kIssueStage && ntile < num_tiles) load_halo(ntile, nchunk);
                 }
-                pre_st = 0;
                 tile = ntile;
                 chunk = nchunk;
             }
@@ -262,9 +264,6 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
         uint8_t* sout = sout0 + grp * L::kStagingBuf;
         const int bar_id = 1 + grp;
         const bool issuer = (q == 0 && lane == 0);  // the group's TMA-store thread
-        sbias[et] = et < p.cout ? p.bias[et] : 0.f; // (both groups write the same values; each syncs on its own barrier)
-        pdl_wait();                                 // amax / sampler state / activations belong to the previous kernels
-        named_bar_sync(bar_id, 128);
         for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x) {
             const int tx = tile % tiles_x;
             const int ty = (tile / tiles_x) % tiles_y;

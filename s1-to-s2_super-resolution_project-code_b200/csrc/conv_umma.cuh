@@ -244,9 +244,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     const int k_iters = (p.taps_w * p.taps_w * p.chunks) / BOXES;
     const int pad = p.taps_w >> 1;
 
-    // Programmatic dependent launch: the next kernel of the stream may be scheduled from now on (its CTAs start as SMs
-    // free up and run their own prologue); it orders itself behind this grid's memory operations with griddepcontrol.wait.
-    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmap_a);
         tma_prefetch_desc(&p.tmap_b);
@@ -271,18 +268,20 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         mbar_fence_init();
     }
     if (warp == 2) { if constexpr (kPair) tmem_alloc_pair<512>(tmem_slot); else tmem_alloc<512>(tmem_slot); }
+    {   // bias for every N tile of this layer, staged once
+        const int nb = p.num_n_tiles * BLOCK_N;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) sbias[i] = p.bias[i];
+    }
     tc_fence_before();
     __syncthreads();
     if constexpr (kPair) cluster_sync_all();    // peer's barriers are initialised before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // Everything above touched only shared memory, TMEM and the tensor maps: under programmatic dependent launch it
-    // overlaps the previous kernel's tail.  What depends on the previous kernel -- activations, amax, the sampler state --
-    // is read / written only behind a griddepcontrol.wait, which every role below executes for itself: the producer after
-    // it has requested the first weight tiles (weights and bias are constant over the whole chain), the epilogue warps
-    // after staging the bias.  The MMA warp touches shared memory and TMEM only.
+    // Everything above touched only shared memory, TMEM and constant data (tensor maps, bias): under programmatic dependent
+    // launch it overlaps the previous kernel's tail.  Activations, amax and the sampler state are read / written below.
+    pdl_launch_dependents();
+    pdl_wait();
     if (warp == 3 && blockIdx.x == 0 && p.amax_zero != nullptr) {       // (warp 3 has no other role)
-        pdl_wait();
         for (int b = lane; b < p.B; b += 32) p.amax_zero[b] = 0u;
     }
 
@@ -310,19 +309,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             if (++sa == kHaloSlots) { sa = 0; pha ^= 1; }
         };
         int tile = cluster_id, chunk = 0;
-        auto load_weights = [&](int tile_, int kcol) {     // one ring stage: TPS weight tiles of one channel chunk
-            const int b_row0 = (tile_ % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            const uint32_t bar = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
-            if (elect_one()) {
-                if (rank == 0) mbar_expect_tx(&full_bar[s], CTAS * L::kStage);
-#pragma unroll
-                for (int j = 0; j < TPS; ++j)
-                    tma_load_2d_g<kPair>(stage_base + s * L::kStage + j * L::kBBox, &p.tmap_b, bar, kcol + j * p.tap_kstride, b_row0);
-            }
-            __syncwarp();
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-        };
         if constexpr (WRES) {                     // one N tile, one chunk per tap: all weights of the layer, once
             const uint32_t bar = kPair ? mapa_shared(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
             if (elect_one()) {
@@ -334,14 +320,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             }
             __syncwarp();
         }
-        // weight tiles of the first (tile, chunk) position go out BEFORE the wait on the previous kernel: they do not depend
-        // on it, and at small batches a launch is short enough for this first round trip to L2 / HBM to matter
-        int pre_taps = 0;
-        if constexpr (!WRES) {
-            if (tile < num_tiles)
-                for (; pre_taps < 9 && pre_taps < STAGES * TPS; pre_taps += TPS) load_weights(tile, pre_taps * p.tap_kstride);
-        }
-        pdl_wait();
         // the halo cursor runs kAhead = HSLOTS - 2 positions ahead of the weight stream: the slot it targets was freed two
         // positions earlier, so the request never blocks on the MMA warp while the weight ring still has work queued
         constexpr int kAhead = kHaloSlots - 2;
@@ -352,9 +330,20 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
         while (tile < num_tiles) {
             if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
-            if constexpr (!WRES) {
-                for (int tap = pre_taps; tap < 9; tap += TPS) load_weights(tile, chunk * KBOX + tap * p.tap_kstride);
-                pre_taps = 0;
+            const int b_row0 = (tile % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
+            int kcol = chunk * KBOX;
+            for (int tap = 0; tap < (WRES ? 0 : 9); tap += TPS, kcol += TPS * p.tap_kstride) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const uint32_t bar = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], CTAS * L::kStage);
+#pragma unroll
+                    for (int j = 0; j < TPS; ++j)
+                        tma_load_2d_g<kPair>(stage_base + s * L::kStage + j * L::kBBox, &p.tmap_b, bar,
+                                             kcol + j * p.tap_kstride, b_row0);
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
             advance(tile, chunk);
         }
@@ -445,25 +434,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         int s = 0;
         uint32_t ph = 0;
         int issued = 0;
-        // The first ring stages of this CTA's first tile get their WEIGHT boxes before the wait on the previous kernel (the
-        // stage's barrier already expects the activation bytes too, which follow right after the wait).
-        int pre = 0;
-        if (cluster_id < num_tiles && p.chunks >= BOXES && p.perf_mode == 0) {
-            const int b_row0 = (cluster_id % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
-            const int npre = k_iters < STAGES ? k_iters : STAGES;
-            for (; pre < npre; ++pre) {
-                const uint32_t full_leader = kPair ? mapa_shared(smem_u32(&full_bar[pre]), 0) : smem_u32(&full_bar[pre]);
-                if (elect_one()) {
-                    if (rank == 0) mbar_expect_tx(&full_bar[pre], CTAS * BOXES * (L::kABox + L::kBBox));
-#pragma unroll
-                    for (int b = 0; b < BOXES; ++b)
-                        tma_load_2d_g<kPair>(stage_base + pre * L::kStage + BOXES * L::kABox + b * L::kBBox, &p.tmap_b, full_leader,
-                                             (pre * BOXES + b) * KBOX, b_row0);
-                }
-                __syncwarp();
-            }
-        }
-        pdl_wait();
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int n_tile = tile % p.num_n_tiles;
             const int m_tile = CTAS * (tile / p.num_n_tiles) + static_cast<int>(rank);
@@ -476,15 +446,14 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             const int b_row0 = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
             int chunk = 0, kx = 0, ky = 0, kcol = 0;             // running (tap, chunk) position, no divisions
             for (int it = 0; it < k_iters; ++it, ++issued) {
-                const bool b_done = issued < pre;                // this stage's weights are already in flight (slot was free)
-                if (!b_done) mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_wait(&empty_bar[s], ph ^ 1);
                 const bool load_a = !((p.perf_mode & 1) && issued >= STAGES);
-                const bool load_b = !((p.perf_mode & 2) && issued >= STAGES) && !b_done;
+                const bool load_b = !((p.perf_mode & 2) && issued >= STAGES);
                 uint8_t* a_dst = stage_base + s * L::kStage;
                 uint8_t* b_dst = a_dst + BOXES * L::kABox;
                 const uint32_t full_leader = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
                 if (elect_one()) {
-                    if (rank == 0 && !b_done)
+                    if (rank == 0)
                         mbar_expect_tx(&full_bar[s], CTAS * BOXES * ((load_a ? L::kABox : 0) + (load_b ? L::kBBox : 0)));
 #pragma unroll
                     for (int b = 0; b < BOXES; ++b) {
@@ -552,12 +521,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         constexpr int kChunks = BLOCK_N / 32;
         constexpr int kChunksWg = (kChunks + EPIWG - 1) / EPIWG;
         const int c_lo = EPIWG == 1 ? 0 : ((warp - 4) >> 2) * kChunksWg;
-        {   // bias for every N tile of this layer (constant over the chain), staged once by the epilogue warps themselves
-            const int nb = p.num_n_tiles * BLOCK_N;
-            for (int i = threadIdx.x - 128; i < nb; i += 128 * EPIWG) sbias[i] = p.bias[i];
-            pdl_wait();                                  // amax / sampler state below belong to the previous kernels
-            named_bar_sync(1, 128 * EPIWG);
-        }
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const int tw = 1 << p.tw_log2;

@@ -69,10 +69,11 @@ def lib():
     """The loaded library (loads on first use; raises if it is not built)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise S1S2Error(f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+        path = os.environ.get("S1S2_LIB", LIB_PATH)      # override: same-box A/B of two builds (measurement aid)
+        if not os.path.exists(path):
+            raise S1S2Error(f"{path} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                             "s1s2_b200 has no CPU or PyTorch fallback")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
