@@ -80,6 +80,9 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (warp == 0) S1S2_TL(0);
+    S1S2_TL_GRID(12, atomicMin);
+    [[maybe_unused]] bool tl_a = true, tl_b = true, tl_c = true;
     const int tiles_x = p.W >> 3, tiles_y = (p.H + 31) >> 5;
     const int num_tiles = tiles_x * tiles_y * p.B;
 
@@ -109,8 +112,9 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) S1S2_TL(1);
     pdl_launch_dependents();                    // see conv_umma_kernel: the prologue above overlaps the previous kernel's tail
-    pdl_wait();
+    if (warp != 0) pdl_wait();                  // the producer waits after it has requested its first weight tiles
 
     if (warp == 0) {
         // ================================================================= TMA producer
@@ -137,12 +141,35 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
         };
         int tile = blockIdx.x, chunk = 0;
         auto advance = [&](int& t, int& c) { if (++c == p.chunks) { c = 0; t += gridDim.x; } };
+        // One ring stage of weight tiles (TPS taps of one channel chunk); `wait` = the slot may still be in use.
+        auto weight_stage = [&](int kcol, bool wait) {
+            if (wait) mbar_wait(&empty_bar[s], ph ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(&full_bar[s], L::kStage);
+#pragma unroll
+                for (int j = 0; j < TPS; ++j)
+                    tma_load_2d(stage_base + s * L::kStage + j * L::kABox, &p.tmap_b, &full_bar[s], kcol + j * p.tap_kstride, 0);
+            }
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+        };
+        // weight tiles of the first (tile, chunk) position go out before the wait on the previous kernel (conv_umma_kernel)
+        int st0 = 0;
+        if (HSLOTS >= 3 && tile < num_tiles)             // (the two-slot walk below interleaves halo requests with the stages)
+            for (; st0 < kStagesPerChunk && st0 < STAGES; ++st0) weight_stage(st0 * TPS * p.tap_kstride, false);
+        pdl_wait();
+        S1S2_TL(2);
         if constexpr (HSLOTS >= 3) {
             // the halo cursor runs HSLOTS - 2 positions ahead of the weight stream (its slot was freed two positions earlier)
             constexpr int kAhead = HSLOTS - 2;
             int htile = tile, hchunk = 0;
             for (int d = 0; d < kAhead; ++d)
                 if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
+            if (tile < num_tiles) {                      // the first position, peeled: its first weight stages are in flight
+                if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
+                for (; st0 < kStagesPerChunk; ++st0) weight_stage(st0 * TPS * p.tap_kstride, true);
+                advance(tile, chunk);
+            }
             while (tile < num_tiles) {
                 if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
                 int kcol = chunk * KBOX;
@@ -198,6 +225,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
             const uint32_t d_tmem = tmem_base + acc * kAccStride;
             for (int chunk = 0; chunk < p.chunks; ++chunk) {
                 mbar_wait(&hfull_bar[sh], phh);
+                S1S2_TL_ONCE(tl_a, 4);
                 const uint32_t h_addr = h0 + sh * L::kHaloSlot;
                 if constexpr (TPS == 1) {
                     for (int tap = 0; tap < 9; ++tap) {
@@ -227,6 +255,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
 #pragma unroll
                     for (int t0 = 0; t0 < 9; t0 += TPS) {
                         mbar_wait(&full_bar[s], ph);
+                        S1S2_TL_ONCE(tl_b, 5);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint64_t adesc_s = umma_smem_desc<kRowBytes>(w0 + s * L::kStage);
@@ -254,6 +283,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
             acc ^= 1;
             if (acc == 0) acc_ph ^= 1;
         }
+        S1S2_TL(6);
     } else if (warp >= 4) {
         // ================================================================= epilogue
         const int q = warp & 3;                     // TMEM lane quadrant = 32 output channels
@@ -277,6 +307,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
             }
 
             mbar_wait(&tfull_bar[acc], acc_ph);
+            if (warp == 4) S1S2_TL_ONCE(tl_c, 7);
             tc_fence_after();
             const StepCoef& sc = p.head.step;
             const size_t plane = static_cast<size_t>(p.H) * p.W;
@@ -420,9 +451,11 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
             }
             acc_ph ^= 1;                            // this group's accumulator is used once per two tiles
         }
+        if (warp == 4) S1S2_TL(8);
         if constexpr (MODE == MODE_STORE) {
             if (issuer) bulk_wait_read0();       // see conv_umma_kernel: writes are ordered by grid completion
         }
+        if (warp == 4) S1S2_TL(9);
     }
 
     tc_fence_before();
@@ -431,6 +464,8 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
+    if (warp == 0) S1S2_TL(10);
+    S1S2_TL_GRID(13, atomicMax);
 }
 
 }  // namespace s1s2

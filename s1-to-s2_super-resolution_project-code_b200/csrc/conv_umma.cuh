@@ -98,7 +98,30 @@ struct ConvParams {
     int perf_mode;                // measurement aid (s1s2_debug_loop_layer): bit 0 / bit 1 = stop re-loading A / B
                                   // once every ring slot has been filled (results are garbage, timing is not)
     HeadParams head;              // MODE_HEAD only
+#ifdef S1S2_TIMELINE
+    unsigned long long* dbg;      // timeline build only (tools/timeline.py): 16 globaltimer stamps of this launch
+#endif
 };
+
+// Timeline build (-DS1S2_TIMELINE, never the shipped library): CTA 0 stamps %globaltimer at the hand-over points of its
+// roles, every CTA folds its entry / exit time into slots 12 / 13.  Slots: 0 entry, 1 prologue done, 2 past
+// griddepcontrol.wait, 3 first loads requested, 4 first activation tile landed, 5 first weight stage landed, 6 last MMA
+// issued, 7 first accumulator complete, 8 last tile's stores issued, 9 stores drained, 10 CTA 0 done.
+#ifdef S1S2_TIMELINE
+#define S1S2_TL(slot)                                                                               \
+    do {                                                                                            \
+        if (p.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.dbg[slot] = globaltimer_ns(); \
+    } while (0)
+#define S1S2_TL_ONCE(flag, slot) do { if (flag) { S1S2_TL(slot); flag = false; } } while (0)
+#define S1S2_TL_GRID(slot, op)                                                                      \
+    do {                                                                                            \
+        if (p.dbg != nullptr && threadIdx.x == 0) op(p.dbg + slot, static_cast<unsigned long long>(globaltimer_ns())); \
+    } while (0)
+#else
+#define S1S2_TL(slot) do { } while (0)
+#define S1S2_TL_ONCE(flag, slot) do { } while (0)
+#define S1S2_TL_GRID(slot, op) do { } while (0)
+#endif
 
 // Halo mode (3x3 layers with Cin % 64 == 0): the M tile is 8 wide x 16 tall and its activations are fetched ONCE per
 // 64-channel chunk as an 18 x 10 pixel halo tile; the nine taps read it through UMMA descriptors whose start address
@@ -236,6 +259,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (warp == 0) S1S2_TL(0);
+    S1S2_TL_GRID(12, atomicMin);
+    [[maybe_unused]] bool tl_a = true, tl_b = true, tl_c = true;
     const uint32_t rank = kPair ? cluster_ctarank() : 0u;
     const int cluster_id = blockIdx.x / CTAS;
     const int num_clusters = gridDim.x / CTAS;
@@ -277,10 +303,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     if constexpr (kPair) cluster_sync_all();    // peer's barriers are initialised before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) S1S2_TL(1);
     // Everything above touched only shared memory, TMEM and constant data (tensor maps, bias): under programmatic dependent
     // launch it overlaps the previous kernel's tail.  Activations, amax and the sampler state are read / written below.
     pdl_launch_dependents();
-    pdl_wait();
+    if (!(HALO && warp == 0)) pdl_wait();       // the halo-mode producer waits after it has requested its first weight tiles
     if (warp == 3 && blockIdx.x == 0 && p.amax_zero != nullptr) {       // (warp 3 has no other role)
         for (int b = lane; b < p.B; b += 32) p.amax_zero[b] = 0u;
     }
@@ -320,6 +347,31 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             }
             __syncwarp();
         }
+        // Weight tiles of the first (tile, chunk) position are requested BEFORE the wait on the previous kernel: weights do
+        // not depend on it, and at small batches they come from HBM (the activations of a model call push them out of L2),
+        // ~1.3 us that would otherwise sit between the dependency release and the first MMA (tools/timeline.py).  The
+        // ring slots are free at kernel start, so no empty-barrier wait is needed here.
+        // One ring stage of weight tiles (TPS taps of one channel chunk); `wait` = the slot may still be in use.
+        auto weight_stage = [&](int b_row0, int kcol, bool wait) {
+            if (wait) mbar_wait(&empty_bar[s], ph ^ 1);
+            const uint32_t bar = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
+            if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(&full_bar[s], CTAS * L::kStage);
+#pragma unroll
+                for (int j = 0; j < TPS; ++j)
+                    tma_load_2d_g<kPair>(stage_base + s * L::kStage + j * L::kBBox, &p.tmap_b, bar, kcol + j * p.tap_kstride, b_row0);
+            }
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+        };
+        [[maybe_unused]] int tap0 = 0;
+        [[maybe_unused]] const int b_row_first = (tile % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
+        if constexpr (!WRES) {
+            if (tile < num_tiles)
+                for (; tap0 < 9 && tap0 < STAGES * TPS; tap0 += TPS) weight_stage(b_row_first, tap0 * p.tap_kstride, false);
+        }
+        pdl_wait();
+        S1S2_TL(2);
         // the halo cursor runs kAhead = HSLOTS - 2 positions ahead of the weight stream: the slot it targets was freed two
         // positions earlier, so the request never blocks on the MMA warp while the weight ring still has work queued
         constexpr int kAhead = kHaloSlots - 2;
@@ -328,6 +380,14 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         auto advance = [&](int& t, int& c) { if (++c == p.chunks) { c = 0; t += num_clusters; } };
         for (int d = 0; d < kAhead; ++d)
             if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
+        S1S2_TL(3);
+        if constexpr (!WRES) {                    // the first position, peeled: its first weight stages are already in flight
+            if (tile < num_tiles) {
+                if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
+                for (; tap0 < 9; tap0 += TPS) weight_stage(b_row_first, tap0 * p.tap_kstride, true);
+                advance(tile, chunk);
+            }
+        }
         while (tile < num_tiles) {
             if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
             const int b_row0 = (tile % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
@@ -362,6 +422,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 const uint32_t d_tmem = tmem_base + acc * kAccStride;
                 for (int chunk = 0; chunk < p.chunks; ++chunk) {
                     mbar_wait(&afull_bar[sa], pha);
+                    S1S2_TL_ONCE(tl_a, 4);
                     const uint32_t a_addr = a0 + sa * Halo<KBOX>::kSlot;
                     // halo descriptor: rows kRowBytes apart, 8-row groups (= image rows of the 8-wide tile) 10 rows apart
                     uint64_t adesc0 = static_cast<uint64_t>(1) << 16;
@@ -371,6 +432,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     if constexpr (TPS == 1) {
                         for (int tap = 0; tap < 9; ++tap) {
                             mbar_wait(&full_bar[s], ph);
+                            S1S2_TL_ONCE(tl_b, 5);
                             tc_fence_after();
                             const int ky = tap / 3, kx = tap - 3 * ky;
                             const uint32_t a_tap = a_addr + (ky * kHaloW + kx) * kRowBytes;
@@ -400,6 +462,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                             } else {
                                 mbar_wait(&full_bar[s], ph);
                             }
+                            S1S2_TL_ONCE(tl_b, 5);
                             tc_fence_after();
                             if (elect_one()) {
                                 const uint64_t bdesc_s = umma_smem_desc<kRowBytes>(b0 + (WRES ? 0 : s) * L::kStage);
@@ -428,12 +491,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 acc ^= 1;
                 if (acc == 0) acc_ph ^= 1;
             }
+            S1S2_TL(6);
         }
     } else if (warp == 0) {
         // ================================================================= TMA producer (both CTAs)
         int s = 0;
         uint32_t ph = 0;
         int issued = 0;
+        S1S2_TL(2);
+        S1S2_TL(3);
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int n_tile = tile % p.num_n_tiles;
             const int m_tile = CTAS * (tile / p.num_n_tiles) + static_cast<int>(rank);
@@ -491,6 +557,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 const uint32_t d_tmem = tmem_base + acc * kAccStride;
                 for (int it = 0; it < k_iters; ++it) {
                     mbar_wait(&full_bar[s], ph);
+                    S1S2_TL_ONCE(tl_b, 5);
                     tc_fence_after();
                     const uint32_t a_addr = stage0 + s * L::kStage;
                     const uint32_t b_addr = a_addr + BOXES * L::kABox;
@@ -514,6 +581,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 acc ^= 1;
                 if (acc == 0) acc_ph ^= 1;
             }
+            S1S2_TL(6);
         }
     } else if (warp >= 4) {
         // ================================================================= epilogue (1 pixel per thread; with two
@@ -551,6 +619,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             }
 
             mbar_wait(&tfull_bar[acc], acc_ph);
+            if (warp == 4) S1S2_TL_ONCE(tl_c, 7);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
             const float* bias_t = sbias + n_tile * BLOCK_N;
@@ -722,6 +791,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             acc ^= 1;
             if (acc == 0) acc_ph ^= 1;
         }
+        if (warp == 4) S1S2_TL(8);
     }
 
     if constexpr (kTmaStore) {
@@ -729,13 +799,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         // ordered by grid completion (what the next kernel's griddepcontrol.wait / stream order waits for)
         if (warp == 4 && lane == 0) bulk_wait_read0();
     }
+    if (warp == 4) S1S2_TL(9);
     tc_fence_before();
     __syncthreads();
-    if constexpr (kPair) cluster_sync_all();    // both CTAs are done with each other's shared memory and TMEM
+    if constexpr (kPair) cluster_sync_exec();   // both CTAs are done with each other's shared memory and TMEM
     if (warp == 2) {
         tc_fence_after();
         if constexpr (kPair) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
     }
+    if (warp == 0) S1S2_TL(10);
+    S1S2_TL_GRID(13, atomicMax);
 }
 
 }  // namespace s1s2

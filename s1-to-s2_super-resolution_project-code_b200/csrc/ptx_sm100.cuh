@@ -145,6 +145,13 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only rendezvous of the cluster (no memory ordering implied: for the end of a kernel, where all that matters is
+// that no CTA leaves while its peer may still address its shared memory / barriers).
+__device__ __forceinline__ void cluster_sync_exec() {
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 // arrive on an mbarrier given by a shared::cluster address (own or peer CTA).  Default semantics (release at CTA
 // scope): what is being published is "this warp has drained its TMEM lanes", already ordered by
 // tcgen05.fence::before_thread_sync; a cluster-scope release costs a MEMBAR.ALL.GPU + ERRBAR per warp per tile.

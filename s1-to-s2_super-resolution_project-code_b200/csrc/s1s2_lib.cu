@@ -336,6 +336,9 @@ struct s1s2_handle {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
                 ev_out[2] = {nullptr, nullptr}, ev_entry = nullptr;
     unsigned long long* sat_counts = nullptr;                      // [views] scratch of s1s2_debug_saturation_count
+#ifdef S1S2_TIMELINE
+    unsigned long long* tl_dbg = nullptr;                          // [layers][16] stamps of the chain being traced, or nullptr
+#endif
 };
 
 namespace {
@@ -625,6 +628,9 @@ int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, uint3
     p.B = B;
     p.amax_in = amax_in;
     p.amax_zero = amax_zero;
+#ifdef S1S2_TIMELINE
+    p.dbg = h->tl_dbg != nullptr ? h->tl_dbg + 16 * (&L - h->layers.data()) : nullptr;
+#endif
     int grid;
     if (k.px) {
         const int tiles = (p.W >> 3) * ((p.H + 31) >> 5) * B;
@@ -1409,6 +1415,40 @@ int s1s2_debug_saturation_count(s1s2_handle* h, int B, uint64_t* counts, int n_o
     CK(cudaStreamSynchronize(st));
     return S1S2_OK;
 }
+
+#ifdef S1S2_TIMELINE
+// Timeline build only (tools/timeline.py; not declared in the public header): runs `calls` model calls back to back
+// exactly like s1s2_sample's loop (programmatic dependent launches, no events in between) and returns the %globaltimer
+// stamps of the LAST call, out[layers][16] (host).
+int s1s2_debug_timeline(s1s2_handle* h, int B, int calls, uint64_t* out, void* stream) {
+    int rc = check_batch(h, B);
+    if (rc != S1S2_OK) return rc;
+    std::string* err = &h->err;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const size_t n = h->layers.size() * 16;
+    unsigned long long* buf = nullptr;
+    CK(cudaMalloc(&buf, n * sizeof(unsigned long long)));
+    std::vector<unsigned long long> init(n, 0ull);
+    for (size_t l = 0; l < h->layers.size(); ++l) init[l * 16 + 12] = ~0ull;
+    HeadParams io;
+    memset(&io, 0, sizeof(io));
+    io.step.kind = STEP_NONE;
+    for (int c = 0; c < calls && rc == S1S2_OK; ++c) {
+        if (c == calls - 1) {
+            cudaMemcpyAsync(buf, init.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, st);
+            cudaStreamSynchronize(st);
+            h->tl_dbg = buf;
+        }
+        rc = run_network(h, B, io, nullptr, nullptr, st, err);
+    }
+    h->tl_dbg = nullptr;
+    cudaStreamSynchronize(st);
+    if (rc == S1S2_OK) cudaMemcpy(out, buf, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    return rc;
+}
+#endif
 
 const char* s1s2_view_name(const s1s2_handle* h, int i) {
     if (h == nullptr || i < 0 || i >= static_cast<int>(h->views.size())) return nullptr;
