@@ -323,7 +323,7 @@ def script_style_v_ddim(model, cond, abar_d, noise, idxs):
     return torch.clamp(x, 0.0, 1.0)
 
 
-def latency_table(model, abar, dev, batches=(1, 2, 4, 8, 16), target_s=0.4):
+def latency_table(model, abar, dev, batches=(1, 2, 4, 8, 16), target_s=0.8):
     """DDIM-50 at small batches (the reference scripts run batch 1): per batch the fused loop (s1s2_sample: one library call
     enqueues 50 model calls) and the script-style drop-in loop; device time by CUDA events over whole chains, plus the host
     time spent enqueueing (when it exceeds the device time the path is launch-bound)."""
@@ -352,7 +352,8 @@ def latency_table(model, abar, dev, batches=(1, 2, 4, 8, 16), target_s=0.4):
             host_one = time.perf_counter() - t0
             torch.cuda.synchronize()
             one = e0.elapsed_time(e1) / 1e3
-            reps = max(2, min(40, int(target_s / max(one, 1e-4))))
+            reps = max(2, min(80, int(target_s / max(one, 1e-4))))
+            clocks = ClockSampler(dev.index or 0)
             t0 = time.perf_counter()
             e0.record()
             for _ in range(reps):
@@ -360,12 +361,14 @@ def latency_table(model, abar, dev, batches=(1, 2, 4, 8, 16), target_s=0.4):
             e1.record()
             host = time.perf_counter() - t0
             torch.cuda.synchronize()
+            clk = clocks.stop()
             ms_chain = e0.elapsed_time(e1) / reps
             assert bool(torch.isfinite(out).all())
             tf = FLOP_PER_CALL * N_CALLS * B / (ms_chain / 1e3) / 1e12
             row[name] = {"chains_timed": reps, "ms_per_chain": round(ms_chain, 3), "ms_per_model_call": round(ms_chain / N_CALLS, 4),
                          "patches_per_s": round(B / (ms_chain / 1e3), 2), "tflops": round(tf, 1), "frac_of_peak": round(tf / peak_tf, 4),
-                         "host_enqueue_ms_per_chain": round(host / reps * 1e3, 3), "first_chain_host_ms": round(host_one * 1e3, 3)}
+                         "host_enqueue_ms_per_chain": round(host / reps * 1e3, 3), "first_chain_host_ms": round(host_one * 1e3, 3),
+                         "sm_mhz": clk.get("sm_mhz"), "power_w_max": clk.get("power_w_max"), "clock_reasons": clk.get("reasons")}
         if B == 1:
             res_f = samplers.run_steps(model, steps, cond, noise, init_scale=init_scale)
             res_d = script_style_v_ddim(model, cond, abar_d, noise, idxs)

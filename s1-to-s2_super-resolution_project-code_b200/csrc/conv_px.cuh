@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
     pdl_launch_dependents();                    // see conv_umma_kernel: the prologue above overlaps the previous kernel's tail
     if (warp != 0) pdl_wait();                  // the producer waits after it has requested its first weight tiles
 
+    if (warp == 3) prefetch_next_weights(p.next_w, p.next_w_bytes, lane);      // (warp 3 has no other role)
     if (warp == 0) {
         // ================================================================= TMA producer
         // flat walk over (tile, chunk).  With two halo slots the NEXT halo tile is requested after weight tile kIssueTap

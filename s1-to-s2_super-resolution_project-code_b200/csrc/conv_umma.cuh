@@ -84,6 +84,8 @@ struct ConvParams {
     const float* bias;            // [num_n_tiles * BLOCK_N]
     const uint32_t* amax_in;      // [B] float bits of max|x_t| per patch for this call (nullptr: scale 1)
     uint32_t* amax_zero;          // first layer only, nullable: [B] words cleared for this call's head to reduce max|x_next| into
+    const uint8_t* next_w;        // weights of the NEXT launch of the chain (nullable) and their size: prefetched into L2
+    uint32_t next_w_bytes;        //   while this kernel runs (see prefetch_next_weights)
     __half* out;                  // NHWC fp16 destination (channel offset already applied)
     int out_cpitch;               // elements between consecutive destination pixels
     int H, W, B;                  // input image size, live batch
@@ -162,6 +164,21 @@ __device__ __forceinline__ void philox_normal4(const HeadParams& hp, uint32_t pi
         z[2 * i] = r * cs;
         z[2 * i + 1] = r * sn;
     }
+}
+
+// At small batches the activations of one model call (~123 MB per patch) push the 34.5 MB of weights out of L2, so every
+// kernel would stream its weights from HBM: ~1.5 us of latency under a weight ring that covers ~2 us -- measured as 70-80 %
+// MMA-phase efficiency at batch 1 against 91 % with L2-resident weights (tools/timeline.py).  Each kernel therefore asks
+// L2 for the NEXT kernel's weights (at most 10.6 MB) while it computes: CTA b takes slice b, one idle warp issues it.
+__device__ __forceinline__ void prefetch_next_weights(const uint8_t* w, uint32_t bytes, int lane) {
+    if (w == nullptr) return;
+    const uint32_t per_cta = ((bytes + gridDim.x - 1) / gridDim.x + 4095u) & ~4095u;
+    const uint32_t lo = blockIdx.x * per_cta;
+    if (lo >= bytes) return;
+    const uint32_t n = min(per_cta, bytes - lo);                 // (weight tensors are multiples of 16 bytes)
+    const uint32_t per_lane = ((n + 31u) / 32u + 127u) & ~127u;
+    const uint32_t off = lane * per_lane;
+    if (off < n) bulk_prefetch_l2(w + lo + off, min(per_lane, n - off));
 }
 
 template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, int SBUF = 1, int TPS = 1,
@@ -308,8 +325,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     // launch it overlaps the previous kernel's tail.  Activations, amax and the sampler state are read / written below.
     pdl_launch_dependents();
     if (!(HALO && warp == 0)) pdl_wait();       // the halo-mode producer waits after it has requested its first weight tiles
-    if (warp == 3 && blockIdx.x == 0 && p.amax_zero != nullptr) {       // (warp 3 has no other role)
-        for (int b = lane; b < p.B; b += 32) p.amax_zero[b] = 0u;
+    if (warp == 3) {                                                    // (warp 3 has no other role)
+        if (blockIdx.x == 0 && p.amax_zero != nullptr)
+            for (int b = lane; b < p.B; b += 32) p.amax_zero[b] = 0u;
+        prefetch_next_weights(p.next_w, p.next_w_bytes, lane);
     }
 
     // Both issue loops below run WARP-UNIFORM (all 32 lanes wait on the barriers and keep the loop state; one

@@ -97,6 +97,11 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
         : "memory");
 }
 
+// Asynchronous prefetch of `bytes` (multiple of 16) at `src` (16-byte aligned) into L2; no completion tracking.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
+}
+
 // TMA store (shared -> global, bulk-group completion).  Out-of-bounds parts of the box are clipped.
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile(

@@ -298,6 +298,7 @@ struct Layer {
     __half* dst;             // output view (channel offset applied)
     int dst_pitch;
     __half* w = nullptr;
+    size_t w_bytes = 0;
     float* bias = nullptr;
     ConvParams p;
     // Alternative tilings of the same layer (same weights, same arithmetic per output element): narrower N tiles that
@@ -628,6 +629,13 @@ int launch_layer(s1s2_handle* h, Layer& L, int B, const uint32_t* amax_in, uint3
     p.B = B;
     p.amax_in = amax_in;
     p.amax_zero = amax_zero;
+    {   // the next launch of the chain (the first layer again after the last one): its weights are prefetched into L2
+        static const bool no_prefetch = getenv("S1S2_NO_WPREFETCH") != nullptr;
+        const size_t li = static_cast<size_t>(&L - h->layers.data());
+        const Layer& nxt = h->layers[(li + 1) % h->layers.size()];
+        p.next_w = no_prefetch ? nullptr : reinterpret_cast<const uint8_t*>(nxt.w);
+        p.next_w_bytes = static_cast<uint32_t>(nxt.w_bytes);
+    }
 #ifdef S1S2_TIMELINE
     p.dbg = h->tl_dbg != nullptr ? h->tl_dbg + 16 * (&L - h->layers.data()) : nullptr;
 #endif
@@ -873,6 +881,7 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
         void* p;
         if (dmalloc(h, &p, welems * sizeof(__half), err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
         L.w = static_cast<__half*>(p);
+        L.w_bytes = welems * sizeof(__half);
         if (dmalloc(h, &p, static_cast<size_t>(L.ntot) * sizeof(float), err) != S1S2_OK) { s1s2_destroy(h); return S1S2_ERR_CUDA; }
         L.bias = static_cast<float*>(p);
         int rc = build_layer_params(h, L, L.kid, L.p, err);
