@@ -896,6 +896,11 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
                 {"conv3", c3b, 384, 384, 2},         {"up2", cat2, 384, 192, 1},    {"conv2.0", c2a, 192, 192, 1},
                 {"conv2", c2b, 192, 192, 1},         {"up1", cat1, 224, 96, 0},     {"conv1.0", c1a, 96, 96, 0},
                 {"xin16", h->xin16, 16, 16, 0}};
+    {   // first use of the device's stream-ordered memory pool costs ~0.1 s (s1s2_stitch allocates its scratch from it):
+        // pay it here, at model creation, not inside the first stitched scene
+        void* scratch = nullptr;
+        if (cudaMallocAsync(&scratch, 256, nullptr) == cudaSuccess) cudaFreeAsync(scratch, nullptr);
+    }
     if (cudaDeviceSynchronize() != cudaSuccess) {
         set_err(err, "arena initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
         s1s2_destroy(h);
