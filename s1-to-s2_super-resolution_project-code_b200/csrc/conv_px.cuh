@@ -28,7 +28,9 @@ constexpr int kPxHaloW = 10, kPxHaloH = 34;
 
 // TPS: weight tiles (taps) per ring stage, HSLOTS: halo ring depth (see conv_umma_kernel's TPS note: the issue loop is
 // ~300 cycles per stage, so KBOX = 32 stages of one tap = two MMAs were issue-bound).
-template <int KBOX, int STAGES, int TPS = 1, int HSLOTS = 2>
+// NQ: 32-channel quarters of the output (3 for Cout = 96, 2 for Cout = 64): sub-tiles of the staging buffer, TMEM lane
+// quadrants drained in pass 1, and the length NQ * 32 of the hidden row the 1x1 head contracts.
+template <int KBOX, int STAGES, int TPS = 1, int HSLOTS = 2, int NQ = 3>
 struct PxSmem {
     static constexpr int kABox = 128 * KBOX * 2;        // weights: 128 rows (cout, zero-padded past the real rows)
     static constexpr int kHaloBytes = kPxHaloW * kPxHaloH * KBOX * 2;          // pixels: 8 x 32 tile + 1-pixel ring
@@ -36,7 +38,7 @@ struct PxSmem {
     static constexpr int kHaloRing = HSLOTS * kHaloSlot;
     static constexpr int kStage = TPS * kABox;          // the ring streams weight tiles only
     static constexpr int kSubBytes = 128 * 64;          // [128 pixels = half a tile][32 ch] fp16, 64B swizzle
-    static constexpr int kStagingBuf = 3 * kSubBytes;
+    static constexpr int kStagingBuf = NQ * kSubBytes;
     static constexpr int kStaging = 2 * kStagingBuf;    // one buffer per epilogue warpgroup
     static constexpr int kBias = 128 * 4;
     static constexpr int kBytes = 1024 + kHaloRing + STAGES * kStage + kStaging + kBias + 256;
@@ -52,9 +54,11 @@ struct PxSmem {
 // accumulator g, staging buffer g and named barrier 1+g and handles every other tile of the CTA.
 constexpr int kPxThreads = 384;
 
-template <int KBOX, int STAGES, int MODE, int TPS = 1, int HSLOTS = 2>
+template <int KBOX, int STAGES, int MODE, int TPS = 1, int HSLOTS = 2, int NQ = 3>
 __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_constant__ ConvParams p) {
-    using L = PxSmem<KBOX, STAGES, TPS, HSLOTS>;
+    using L = PxSmem<KBOX, STAGES, TPS, HSLOTS, NQ>;
+    static_assert(NQ == 2 || NQ == 3, "Cout = 64 or 96");
+    constexpr int kHidden = NQ * 32;            // hidden channels = Cout of this layer = input channels of the 1x1 head
     constexpr int kPxHaloSlots = HSLOTS;
     static_assert(MODE == MODE_STORE || MODE == MODE_HEAD, "conv_px_kernel modes");
     constexpr int kRowBytes = KBOX * 2;
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
                         if (sc.flags & STEP_FLAG_PHILOX) philox_normal4(p.head, static_cast<uint32_t>(pix), static_cast<uint32_t>(n), z4);
                     }
                 }
-                if (q < 3) {
+                if (q < NQ) {
                     // pass 1: this thread's channel, 128 pixels of the half tile -> staging[pixel][channel]
                     const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
                     const float b = sbias[et] * s_dn;
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
                     named_bar_sync(bar_id, 128);
                     if (issuer) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c)
+                        for (int c = 0; c < NQ; ++c)
                             tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, c * 32, tx << 3, (ty << 5) + half * 16, n);
                         bulk_commit();
                     }
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
                     for (int k = 0; k < kHeadOut; ++k) o[k] = p.head.b[k] * s_dn;
                     const int sw = (px >> 1) & 3;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
+                    for (int c = 0; c < NQ; ++c) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const uint4 v = *reinterpret_cast<const uint4*>(sout + c * L::kSubBytes + px * 64 + ((g ^ sw) << 4));
@@ -392,8 +396,8 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
                                 const int ch = c * 32 + g * 8 + e * 2;
 #pragma unroll
                                 for (int k = 0; k < kHeadOut; ++k) {
-                                    o[k] = fmaf(hh.x, p.head.w[k * kHeadIn + ch], o[k]);
-                                    o[k] = fmaf(hh.y, p.head.w[k * kHeadIn + ch + 1], o[k]);
+                                    o[k] = fmaf(hh.x, p.head.w[k * kHidden + ch], o[k]);
+                                    o[k] = fmaf(hh.y, p.head.w[k * kHidden + ch + 1], o[k]);
                                 }
                             }
                         }

@@ -59,11 +59,11 @@ struct StepCoef {
     int flags;
 };
 
-constexpr int kHeadIn = 96;   // conv1.2 output channels == outc input channels (base_ch)
+constexpr int kHeadIn = 96;   // conv1.2 output channels == outc input channels: base_ch (96, or 64 with the unused tail zero)
 constexpr int kHeadOut = 4;
 
 struct HeadParams {
-    float w[kHeadOut * kHeadIn];  // outc.weight [4][96]
+    float w[kHeadOut * kHeadIn];  // outc.weight [4][base_ch], contiguous
     float b[kHeadOut];
     float* x_t;                   // f32 NCHW [B,4,H,W], updated in place (nullptr for a plain forward)
     float* pred_out;              // f32 NCHW eps / v (nullable)

@@ -200,7 +200,7 @@ CUtensorMapSwizzle swizzle_for(int kbox) {
 }
 
 // ---------------------------------------------------------------------------------------------- layers
-enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_PX_STORE, K_PX_HEAD32, K_HSTORE, K_HPOOL, K_HSTORE256, K_HPOOL256, K_HINC, K_HC96IN, K_HSTORE96, K_HPOOL96, K_HHEAD96, K_COUNT };
+enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL256, K_CONVT256, K_N96, K_HEAD, K_PX_STORE, K_PX_HEAD32, K_HSTORE, K_HPOOL, K_HSTORE256, K_HPOOL256, K_HINC, K_HC96IN, K_HSTORE96, K_HPOOL96, K_HHEAD96, K_HINC64, K_HSTORE128, K_HPOOL128, K_HSTORE64, K_PX_HEAD64, K_COUNT };
 
 struct KernelInfo {
     void (*fn)(const ConvParams);
@@ -226,15 +226,15 @@ KernelInfo make_kernel() {
     return k;
 }
 
-template <int KB, int ST, int MODE, int TPS = 1, int HSLOTS = 2>
+template <int KB, int ST, int MODE, int TPS = 1, int HSLOTS = 2, int NQ = 3>
 KernelInfo make_px_kernel() {
     KernelInfo k;
-    k.fn = conv_px_kernel<KB, ST, MODE, TPS, HSLOTS>;
+    k.fn = conv_px_kernel<KB, ST, MODE, TPS, HSLOTS, NQ>;
     k.threads = kPxThreads;
-    k.block_n = 96;
+    k.block_n = 32 * NQ;
     k.kbox = KB;
     k.boxes = 1;
-    k.smem = PxSmem<KB, ST, TPS, HSLOTS>::kBytes;
+    k.smem = PxSmem<KB, ST, TPS, HSLOTS, NQ>::kBytes;
     k.mode = MODE;
     k.ctas = 1;
     k.px = true;
@@ -276,6 +276,14 @@ struct KernelTable {
         t[K_HSTORE96] = make_kernel<96, 64, 1, 6, MODE_STORE, 2, true, false, 1, 3>();
         t[K_HPOOL96] = make_kernel<96, 64, 1, 6, MODE_POOL, 2, true, false, 1, 3>();
         t[K_HHEAD96] = make_kernel<96, 32, 1, 3, MODE_HEAD, 2, true, false, 1, 9>();   // conv1.2: exact 32-channel chunks, nine taps per stage
+        // base_ch = 64 (the class default of Train_Orignal.py:99): channel counts 64 / 128 / 256 / 512.  The 256-column
+        // kernels above serve Cout = 256 / 512 and the three transposed convs; these cover Cout = 128 and 64 (three taps
+        // per stage for the same reason as the 96-column tiles), the first layer and the head.
+        t[K_HINC64] = make_kernel<64, 16, 1, 1, MODE_STORE, 2, true, true, 4, 9, 2, 8>();
+        t[K_HSTORE128] = make_kernel<128, 64, 1, 4, MODE_STORE, 2, true, false, 1, 3>();
+        t[K_HPOOL128] = make_kernel<128, 64, 1, 5, MODE_POOL, 2, true, false, 1, 3>();
+        t[K_HSTORE64] = make_kernel<64, 64, 1, 8, MODE_STORE, 2, true, false, 1, 3>();
+        t[K_PX_HEAD64] = make_px_kernel<32, 4, MODE_HEAD, 3, 3, 2>();
     }
 };
 const KernelInfo* kernel_table() {
@@ -317,6 +325,7 @@ struct View {
 
 struct s1s2_handle {
     int device = 0;
+    int base_ch = 96;
     int H = 0, W = 0, max_batch = 0, nalloc = 0;
     int num_sms = 0;
     bool weights_loaded = false;
@@ -711,9 +720,10 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     std::string* err = &g_error;
     if (out == nullptr) return S1S2_ERR_INVALID;
     *out = nullptr;
-    if (in_ch != 8 || out_ch != 4 || base_ch != 96) {
+    if (in_ch != 8 || out_ch != 4 || (base_ch != 96 && base_ch != 64)) {
         set_err(err, "unsupported architecture (in_ch %d, out_ch %d, base_ch %d): this library implements "
-                     "UNetSmall(8, 4, 96)", in_ch, out_ch, base_ch);
+                     "UNetSmall(8, 4, base_ch) for base_ch = 96 (the scripts' default) and 64 (the class default)", in_ch, out_ch,
+                base_ch);
         return S1S2_ERR_INVALID;
     }
     if (H < 16 || W < 16 || H % 16 != 0 || W % 16 != 0 || max_batch < 1) {
@@ -734,6 +744,7 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     CK(cudaSetDevice(device));
     s1s2_handle* h = new s1s2_handle();
     h->device = device;
+    h->base_ch = base_ch;
     h->H = H;
     h->W = W;
     h->max_batch = max_batch;
@@ -754,12 +765,17 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
 
     const size_t N = static_cast<size_t>(h->nalloc);
     const size_t P0 = static_cast<size_t>(H) * W, P1 = P0 / 4, P2 = P0 / 16, P3 = P0 / 64;
+    // channel counts of the four resolutions; cat1 = [up1 (c1) | inc (c1) | pad]: for base_ch = 96 the pad is 32 channels
+    // that stay zero (the K-padded A/B variant of down1.0.0 reads [inc | zeros] as 128 channels)
+    const int c1 = base_ch, c2 = 2 * base_ch, c4 = 4 * base_ch, c8 = 8 * base_ch;
+    const bool b96 = base_ch == 96;
+    const int cat1p = b96 ? 224 : 2 * c1;
     __half *cat1, *d1a, *cat2, *d2a, *cat3, *d3a, *e4, *c3a, *c3b, *c2a, *c2b, *c1a;
     struct { __half** p; size_t elems; } bufs[] = {
-        {&h->xin16, N * P0 * 16}, {&cat1, N * P0 * 224}, {&d1a, N * P0 * 192}, {&cat2, N * P1 * 384},
-        {&d2a, N * P1 * 384},     {&cat3, N * P2 * 768}, {&d3a, N * P2 * 768}, {&e4, N * P3 * 768},
-        {&c3a, N * P2 * 384},     {&c3b, N * P2 * 384},  {&c2a, N * P1 * 192}, {&c2b, N * P1 * 192},
-        {&c1a, N * P0 * 96}};
+        {&h->xin16, N * P0 * 16}, {&cat1, N * P0 * cat1p}, {&d1a, N * P0 * c2}, {&cat2, N * P1 * c4},
+        {&d2a, N * P1 * c4},      {&cat3, N * P2 * c8},    {&d3a, N * P2 * c8}, {&e4, N * P3 * c8},
+        {&c3a, N * P2 * c4},      {&c3b, N * P2 * c4},     {&c2a, N * P1 * c2}, {&c2b, N * P1 * c2},
+        {&c1a, N * P0 * c1}};
     for (auto& b : bufs) {
         void* p = nullptr;
         if (dmalloc(h, &p, b.elems * sizeof(__half), err) != S1S2_OK) {
@@ -808,33 +824,38 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
         L.src = src; L.src_pitch = sp; L.dst = dst; L.dst_pitch = dp;
         h->layers.push_back(L);
     };
-    //   name          kernel    lvl cin  N     cout taps src          pitch dst           pitch
-    // cat1 = [up1 (96) | inc (96) | 32 channels that stay zero]: down1.0.0 reads [inc | zeros] as Cin = 128 = two
-    // 64-channel chunks (zero weights on the padding) and so runs in halo mode like every other 3x3 layer.
-    add("inc.0",       K_INC,    0,  16,  96,   96,  3,   h->xin16,    16,   cat1 + 96,    224);
+    // Kernel of a 3x3 layer by its output width (non-halo ids: the halo / pixels-on-N substitutions follow below).
+    // base_ch = 96: N = 192 tiles for Cout = 192 / 384, N = 256 for 768.  base_ch = 64: N = 128 for Cout = 128, N = 256 for 256 / 512.
+    const KernelId kS2 = b96 ? K_STORE : K_HSTORE128, kP2 = b96 ? K_POOL : K_HPOOL128;          // Cout = 2 * base_ch
+    const KernelId kS4 = b96 ? K_STORE : K_HSTORE256, kP4 = b96 ? K_POOL : K_HPOOL256;          // Cout = 4 * base_ch
+    const KernelId kS8 = b96 ? K_STORE256 : K_HSTORE256, kP8 = b96 ? K_POOL256 : K_HPOOL256;    // Cout = 8 * base_ch
+    //   name          kernel    lvl cin  N       cout taps src          pitch  dst           pitch
+    add("inc.0",       b96 ? K_INC : K_HINC64, 0, 16, c1, c1, 3, h->xin16, 16,  cat1 + c1,    cat1p);
     h->layers.back().first = true;
-    if (getenv("S1S2_PAD96") != nullptr) {    // A/B: K padded to 128 per tap (two 64-channel chunks, a quarter of the MMAs wasted)
-        add("down1.0.0", K_STORE,  0,  128, 192,  192, 3,   cat1 + 96,   224,  d1a,          192);
+    if (!b96) {
+        add("down1.0.0", kS2,      0,  c1,  c2,     c2,  3,   cat1 + c1,   cat1p, d1a,          c2);
+    } else if (getenv("S1S2_PAD96") != nullptr) {    // A/B: K padded to 128 per tap (two 64-channel chunks, a quarter of the MMAs wasted)
+        add("down1.0.0", K_STORE,  0,  128, c2,     c2,  3,   cat1 + c1,   cat1p, d1a,          c2);
         h->layers.back().cin_real = 96;
     } else {                                   // exact K = 96 per tap as three 32-channel chunks
-        add("down1.0.0", K_C96IN,  0,  96,  192,  192, 3,   cat1 + 96,   224,  d1a,          192);
+        add("down1.0.0", K_C96IN,  0,  c1,  c2,     c2,  3,   cat1 + c1,   cat1p, d1a,          c2);
     }
-    add("down1.0.2",   K_POOL,   0,  192, 192,  192, 3,   d1a,         192,  cat2 + 192,   384);
-    add("down2.0.0",   K_STORE,  1,  192, 384,  384, 3,   cat2 + 192,  384,  d2a,          384);
-    add("down2.0.2",   K_POOL,   1,  384, 384,  384, 3,   d2a,         384,  cat3 + 384,   768);
-    add("down3.0.0",   K_STORE256, 2, 384, 768,  768, 3,  cat3 + 384,  768,  d3a,          768);
-    add("down3.0.2",   K_POOL256, 2, 768, 768,  768, 3,   d3a,         768,  e4,           768);
-    add("up3",         K_CONVT256, 3, 768, 1536, 384, 1,  e4,          768,  cat3,         768);
-    add("conv3.0",     K_STORE,  2,  768, 384,  384, 3,   cat3,        768,  c3a,          384);
-    add("conv3.2",     K_STORE,  2,  384, 384,  384, 3,   c3a,         384,  c3b,          384);
-    add("up2",         K_CONVT256, 2, 384, 768,  192, 1,  c3b,         384,  cat2,         384);
-    add("conv2.0",     K_STORE,  1,  384, 192,  192, 3,   cat2,        384,  c2a,          192);
-    add("conv2.2",     K_STORE,  1,  192, 192,  192, 3,   c2a,         192,  c2b,          192);
-    add("up1",         K_CONVT,  1,  192, 384,  96,  1,   c2b,         192,  cat1,         224);
-    add("conv1.0",     K_N96,    0,  192, 96,   96,  3,   cat1,        224,  c1a,          96);
-    add("conv1.2",     K_HEAD,   0,  96,  96,   96,  3,   c1a,         96,   nullptr,      0);
+    add("down1.0.2",   kP2,      0,  c2,  c2,     c2,  3,   d1a,         c2,    cat2 + c2,    c4);
+    add("down2.0.0",   kS4,      1,  c2,  c4,     c4,  3,   cat2 + c2,   c4,    d2a,          c4);
+    add("down2.0.2",   kP4,      1,  c4,  c4,     c4,  3,   d2a,         c4,    cat3 + c4,    c8);
+    add("down3.0.0",   kS8,      2,  c4,  c8,     c8,  3,   cat3 + c4,   c8,    d3a,          c8);
+    add("down3.0.2",   kP8,      2,  c8,  c8,     c8,  3,   d3a,         c8,    e4,           c8);
+    add("up3",         K_CONVT256, 3, c8, 4 * c4, c4,  1,   e4,          c8,    cat3,         c8);
+    add("conv3.0",     kS4,      2,  c8,  c4,     c4,  3,   cat3,        c8,    c3a,          c4);
+    add("conv3.2",     kS4,      2,  c4,  c4,     c4,  3,   c3a,         c4,    c3b,          c4);
+    add("up2",         K_CONVT256, 2, c4, 4 * c2, c2,  1,   c3b,         c4,    cat2,         c4);
+    add("conv2.0",     kS2,      1,  c4,  c2,     c2,  3,   cat2,        c4,    c2a,          c2);
+    add("conv2.2",     kS2,      1,  c2,  c2,     c2,  3,   c2a,         c2,    c2b,          c2);
+    add("up1",         b96 ? K_CONVT : K_CONVT256, 1, c2, 4 * c1, c1, 1, c2b, c2,    cat1,         cat1p);
+    add("conv1.0",     b96 ? K_N96 : K_HSTORE64, 0, c2, c1, c1,  3,   cat1,        cat1p, c1a,          c1);
+    add("conv1.2",     b96 ? K_HEAD : K_PX_HEAD64, 0, c1, c1, c1, 3,  c1a,         c1,    nullptr,      0);
 
-    if (getenv("S1S2_NO_HALO") == nullptr) {
+    if (b96 && getenv("S1S2_NO_HALO") == nullptr) {
         for (Layer& L : h->layers) {
             if (L.taps_w != 3) continue;
             if (L.kid == K_INC) L.kid = K_HINC;
@@ -846,7 +867,7 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
             else if (L.kid == K_POOL256) L.kid = K_HPOOL256;
         }
     }
-    if (getenv("S1S2_NO_PX") == nullptr) {       // default: pixels-on-N kernels for the Cout = 96 full-resolution layers
+    if (b96 && getenv("S1S2_NO_PX") == nullptr) {       // default: pixels-on-N kernel for the head layer
         for (Layer& L : h->layers) {
             // conv1.0: Cout on N with 96-column tiles, three taps per stage (measured 8 % faster than the pixels-on-N kernel,
             // whose M = 128 MMAs carry 96 real rows; S1S2_C10_PX=1 restores that one for A/B).  conv1.2 + head: pixels on N
@@ -858,7 +879,8 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     if (const char* force = getenv("S1S2_FORCE")) {        // measurement aid: "layer=KERNEL[,layer=KERNEL...]", e.g. conv2.2=HC96IN
         static const struct { const char* name; KernelId kid; } names[] = {
             {"HSTORE", K_HSTORE}, {"HPOOL", K_HPOOL}, {"HSTORE256", K_HSTORE256}, {"HPOOL256", K_HPOOL256}, {"HC96IN", K_HC96IN},
-            {"HSTORE96", K_HSTORE96}, {"HPOOL96", K_HPOOL96}, {"PX_STORE", K_PX_STORE}, {"STORE", K_STORE}, {"N96", K_N96}};
+            {"HSTORE96", K_HSTORE96}, {"HPOOL96", K_HPOOL96}, {"PX_STORE", K_PX_STORE}, {"STORE", K_STORE}, {"N96", K_N96},
+            {"HSTORE128", K_HSTORE128}, {"HPOOL128", K_HPOOL128}, {"HSTORE64", K_HSTORE64}};
         std::string spec = force;
         for (Layer& L : h->layers)
             for (const auto& nm : names) {
@@ -870,10 +892,16 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
     if (getenv("S1S2_NO_ALTS") == nullptr) {     // narrower tilings for small batches (pick_variant), widest first
         for (Layer& L : h->layers) {
             auto alt = [&](KernelId kid) { if (L.ntot % kernel_table()[kid].block_n == 0) L.alts.push_back({kid, ConvParams()}); };
-            if (L.kid == K_HSTORE256) { alt(K_HSTORE); alt(K_HSTORE96); }
-            else if (L.kid == K_HPOOL256) { alt(K_HPOOL); alt(K_HPOOL96); }
-            else if (L.kid == K_HSTORE) alt(K_HSTORE96);
-            else if (L.kid == K_HPOOL) alt(K_HPOOL96);
+            if (b96) {
+                if (L.kid == K_HSTORE256) { alt(K_HSTORE); alt(K_HSTORE96); }
+                else if (L.kid == K_HPOOL256) { alt(K_HPOOL); alt(K_HPOOL96); }
+                else if (L.kid == K_HSTORE) alt(K_HSTORE96);
+                else if (L.kid == K_HPOOL) alt(K_HPOOL96);
+            } else {
+                if (L.kid == K_HSTORE256) { alt(K_HSTORE128); alt(K_HSTORE64); }
+                else if (L.kid == K_HPOOL256) alt(K_HPOOL128);
+                else if (L.kid == K_HSTORE128) alt(K_HSTORE64);
+            }
         }
     }
     for (Layer& L : h->layers) {
@@ -890,11 +918,11 @@ int s1s2_create(s1s2_handle** out, int device, int in_ch, int out_ch, int base_c
         if (rc != S1S2_OK) { s1s2_destroy(h); return rc; }
     }
     // views for s1s2_debug_activation: name = the oracle's tap key
-    h->views = {{"inc", cat1 + 96, 224, 96, 0},      {"down1.0", d1a, 192, 192, 0}, {"down1", cat2 + 192, 384, 192, 1},
-                {"down2.0", d2a, 384, 384, 1},       {"down2", cat3 + 384, 768, 384, 2}, {"down3.0", d3a, 768, 768, 2},
-                {"down3", e4, 768, 768, 3},          {"up3", cat3, 768, 384, 2},    {"conv3.0", c3a, 384, 384, 2},
-                {"conv3", c3b, 384, 384, 2},         {"up2", cat2, 384, 192, 1},    {"conv2.0", c2a, 192, 192, 1},
-                {"conv2", c2b, 192, 192, 1},         {"up1", cat1, 224, 96, 0},     {"conv1.0", c1a, 96, 96, 0},
+    h->views = {{"inc", cat1 + c1, cat1p, c1, 0},    {"down1.0", d1a, c2, c2, 0},   {"down1", cat2 + c2, c4, c2, 1},
+                {"down2.0", d2a, c4, c4, 1},         {"down2", cat3 + c4, c8, c4, 2}, {"down3.0", d3a, c8, c8, 2},
+                {"down3", e4, c8, c8, 3},            {"up3", cat3, c8, c4, 2},      {"conv3.0", c3a, c4, c4, 2},
+                {"conv3", c3b, c4, c4, 2},           {"up2", cat2, c4, c2, 1},      {"conv2.0", c2a, c2, c2, 1},
+                {"conv2", c2b, c2, c2, 1},           {"up1", cat1, cat1p, c1, 0},   {"conv1.0", c1a, c1, c1, 0},
                 {"xin16", h->xin16, 16, 16, 0}};
     {   // first use of the device's stream-ordered memory pool costs ~0.1 s (s1s2_stitch allocates its scratch from it):
         // pay it here, at model creation, not inside the first stitched scene
@@ -946,7 +974,7 @@ int s1s2_load_weights(s1s2_handle* h, int n, const char* const* names, const flo
         return S1S2_ERR_INVALID;
     };
     if (n != 34) {
-        set_err(err, "strict load: expected the 34 tensors of UNetSmall(8,4,96), got %d", n);
+        set_err(err, "strict load: expected the 34 tensors of UNetSmall(8,4,%d), got %d", h->base_ch, n);
         return S1S2_ERR_INVALID;
     }
     for (Layer& L : h->layers) {
@@ -954,9 +982,9 @@ int s1s2_load_weights(s1s2_handle* h, int n, const char* const* names, const flo
         const std::string nm = L.name;
         int rc;
         if (L.first) {
-            if ((rc = find(nm + ".weight", 96 * 9 * 9, &w)) || (rc = find(nm + ".bias", 96, &b))) return rc;
-            repack_inc_kernel<<<64, 256, 0, st>>>(w, L.w, 96);
-            tile_bias_kernel<<<4, 256, 0, st>>>(b, L.bias, 96, 1);
+            if ((rc = find(nm + ".weight", static_cast<int64_t>(L.cout) * 9 * 9, &w)) || (rc = find(nm + ".bias", L.cout, &b))) return rc;
+            repack_inc_kernel<<<64, 256, 0, st>>>(w, L.w, L.cout);
+            tile_bias_kernel<<<4, 256, 0, st>>>(b, L.bias, L.cout, 1);
         } else if (kernel_table()[L.kid].mode == MODE_CONVT) {
             if ((rc = find(nm + ".weight", static_cast<int64_t>(L.cin) * L.cout * 4, &w)) ||
                 (rc = find(nm + ".bias", L.cout, &b)))
@@ -977,8 +1005,9 @@ int s1s2_load_weights(s1s2_handle* h, int n, const char* const* names, const flo
     {
         const float *w = nullptr, *b = nullptr;
         int rc;
-        if ((rc = find("outc.weight", kHeadOut * kHeadIn, &w)) || (rc = find("outc.bias", kHeadOut, &b))) return rc;
-        CK(cudaMemcpyAsync(h->head_w, w, sizeof(h->head_w), cudaMemcpyDeviceToHost, st));
+        if ((rc = find("outc.weight", kHeadOut * h->base_ch, &w)) || (rc = find("outc.bias", kHeadOut, &b))) return rc;
+        memset(h->head_w, 0, sizeof(h->head_w));            // [4][base_ch] contiguous, the layout the head kernels index
+        CK(cudaMemcpyAsync(h->head_w, w, sizeof(float) * kHeadOut * h->base_ch, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h->head_b, b, sizeof(h->head_b), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));

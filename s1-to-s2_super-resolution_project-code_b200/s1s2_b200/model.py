@@ -31,12 +31,12 @@ def _pair(cin, cout):
 class _Engine:
     """One library handle: arena for (H, W, max_batch) on one device + the weights it was loaded with."""
 
-    def __init__(self, device_index, H, W, max_batch):
+    def __init__(self, device_index, H, W, max_batch, base_ch=96):
         self.h = C.c_void_p()
         self.key = (device_index, H, W)
         self.max_batch = max_batch
         self.weights_version = None
-        _lib.check(_lib.lib().s1s2_create(C.byref(self.h), device_index, 8, 4, 96, H, W, max_batch))
+        _lib.check(_lib.lib().s1s2_create(C.byref(self.h), device_index, 8, 4, base_ch, H, W, max_batch))
 
     def close(self):
         if self.h:
@@ -103,8 +103,8 @@ class UNetSmallB200(nn.Module):
         if device.type != "cuda":
             raise _lib.S1S2Error("UNetSmallB200 runs only on a CUDA (sm_100a) device; there is no CPU fallback. "
                                  "Move the model and its inputs to 'cuda'.")
-        if (self.in_ch, self.out_ch, self.base_ch) != (8, 4, 96):
-            raise _lib.S1S2Error("libs1s2_b200 implements UNetSmall(in_ch=8, out_ch=4, base_ch=96) only "
+        if (self.in_ch, self.out_ch) != (8, 4) or self.base_ch not in (64, 96):
+            raise _lib.S1S2Error("libs1s2_b200 implements UNetSmall(in_ch=8, out_ch=4, base_ch=96 | 64) only "
                                  f"(got {self.in_ch}, {self.out_ch}, {self.base_ch})")
         idx = device.index if device.index is not None else torch.cuda.current_device()
         key = (idx, H, W)
@@ -113,7 +113,7 @@ class UNetSmallB200(nn.Module):
             eng.close()
             eng = None
         if eng is None:
-            eng = _Engine(idx, H, W, max(batch, self.max_batch))
+            eng = _Engine(idx, H, W, max(batch, self.max_batch), self.base_ch)
             self._engines[key] = eng
         self._engines.move_to_end(key)           # activation() / saturation_counts() read the engine used last
         ver = self._weights_version()

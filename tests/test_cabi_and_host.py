@@ -45,7 +45,7 @@ def test_no_cpu_fallback(lib):
     m = s1s2_b200.UNetSmallB200(8, 4, 96)
     with pytest.raises(s1s2_b200.S1S2Error):
         m(torch.zeros(1, 8, 32, 32), torch.zeros(1, dtype=torch.long))
-    assert lib.lib().s1s2_create(C.byref(h), 0, 8, 4, 64, 32, 32, 1) == lib.ERR_INVALID     # architecture check first
+    assert lib.lib().s1s2_create(C.byref(h), 0, 8, 4, 48, 32, 32, 1) == lib.ERR_INVALID     # architecture check first
 
 
 def test_step_struct_layout(lib):

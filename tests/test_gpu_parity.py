@@ -114,7 +114,7 @@ def test_drop_in_surface(env):
     with pytest.raises(RuntimeError):
         s1s2_b200.UNetSmallB200(8, 4, 96).load_state_dict(bad, strict=True)
     with pytest.raises(s1s2_b200.S1S2Error):
-        s1s2_b200.UNetSmallB200(8, 4, 64).to(env["dev"])(torch.zeros(1, 8, 32, 32, device="cuda"),
+        s1s2_b200.UNetSmallB200(8, 4, 48).to(env["dev"])(torch.zeros(1, 8, 32, 32, device="cuda"),
                                                       torch.zeros(1, dtype=torch.long, device="cuda"))
     with pytest.raises(s1s2_b200.S1S2Error):
         m(torch.zeros(1, 8, 30, 32, device="cuda"), torch.zeros(1, dtype=torch.long, device="cuda"))     # H % 16

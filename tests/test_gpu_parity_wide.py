@@ -342,3 +342,63 @@ def test_filter_colloc_uses_greater_than_zero_like_build_mask(env):
     assert abs(float(st[0, 0]) - 0.5) < 1e-6
     _, mask, ratio = patch.tile_extract(scn, np.array([[0, 0]], np.int32), 32, vmask=colloc)   # any non-zero value is valid
     assert abs(float(ratio[0]) - 0.75) < 1e-6 and int(mask.sum()) == 24 * 32
+
+
+# ------------------------------------------------------------------------------------------------ base_ch = 64
+@pytest.fixture(scope="module")
+def env64():
+    """UNetSmall(8, 4, 64): the class default of the reference (Train_Orignal.py:99); the scripts pass --base_ch 96."""
+    import s1s2_b200
+    dev = torch.device("cuda:0")
+    sd = ounet.init_state_dict(8, 4, 64, seed=4321)
+    model = s1s2_b200.UNetSmallB200(8, 4, 64, max_batch=4).to(dev)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    _, alphas, abar = osched.make_schedule(1000)
+    return dict(dev=dev, sd=sd, model=model, oracle=ounet.OracleModel(sd), abar=abar, alphas=alphas)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (1, 48, 80), (3, 64, 64), (1, 256, 256)])
+def test_base64_layers_isolated(env64, B, H, W):
+    from layer_ref import check_layers
+    x, cond = _inputs(B, H, W, seed=700 + B * 10 + H)
+    t = torch.tensor([999, 20, 501][:B], dtype=torch.long)
+    y = env64["model"](torch.cat([x, cond], 1).to(env64["dev"]), t.to(env64["dev"]))
+    torch.cuda.synchronize()
+    rows = check_layers(env64["model"], env64["sd"], y, B)
+    bad = [(n, e, m) for n, e, m, _ in rows if not e <= 2.0 ** -9 * m + 1e-6]
+    assert not bad, bad
+
+
+def test_base64_model_call_and_chain_vs_oracle(env64):
+    from s1s2_b200 import schedule
+    dev, ab = env64["dev"], env64["abar"]
+    x, cond = _inputs(1, 256, 256, seed=711)
+    xin = torch.cat([x, cond], 1)
+    t = torch.tensor([999], dtype=torch.long)
+    ref = env64["oracle"](xin, t)
+    got = env64["model"](xin.to(dev), t.to(dev)).cpu()
+    rel = float((got - ref).norm() / ref.norm())
+    assert rel <= 5e-3, rel
+    assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+    # teacher-forced chains: v on grid B (12 calls) and eps on grid A from 999 (8 calls), every update bit-exact
+    x, cond = _inputs(2, 64, 64, seed=712)
+    worst, _ = _teacher_forced_sparse(env64, schedule.steps_grid_b(ab, schedule.grid_b(999, 12), "v"), cond, x,
+                                      float(torch.sqrt(1 - ab[999])), every=1)
+    worst2, _ = _teacher_forced_sparse(env64, schedule.steps_eps_grid_a(ab, 999, 8), cond, x, 1.0, every=1)
+    print(f"[base_ch 64] model call rel-L2 {rel:.2e}; chains: worst per-step rel-L2 {worst:.2e} (v), {worst2:.2e} (eps)")
+
+
+def test_base64_batch_independent(env64):
+    dev = env64["dev"]
+    x, cond = _inputs(4, 64, 64, seed=713)
+    t = torch.tensor([999, 979, 20, 0], dtype=torch.long)
+    xin = torch.cat([x, cond], 1).to(dev)
+    y = env64["model"](xin, t.to(dev)).clone()
+    for i in range(4):
+        assert torch.equal(env64["model"](xin[i:i + 1], t[i:i + 1].to(dev))[0], y[i]), i
+    x, cond = _inputs(3, 256, 256, seed=714)            # small-batch tilings at full size
+    xin = torch.cat([x, cond], 1).to(dev)
+    t = torch.tensor([999, 501, 20], dtype=torch.long).to(dev)
+    y = env64["model"](xin, t).clone()
+    assert torch.equal(env64["model"](xin[1:2], t[1:2])[0], y[1])

@@ -13,9 +13,12 @@ import s1s2_b200  # noqa: E402
 from s1s2_b200 import samplers, schedule  # noqa: E402
 
 
+BASE_CH = int(os.environ.get("S1S2_BASE_CH", "96"))      # 64: the reference's class default
+
+
 def make(max_batch):
-    sd = ounet.init_state_dict(8, 4, 96, seed=1234)
-    m = s1s2_b200.UNetSmallB200(8, 4, 96, max_batch=max_batch).to("cuda")
+    sd = ounet.init_state_dict(8, 4, BASE_CH, seed=1234)
+    m = s1s2_b200.UNetSmallB200(8, 4, BASE_CH, max_batch=max_batch).to("cuda")
     m.load_state_dict(sd)
     return sd, m.eval()
 
@@ -50,8 +53,9 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        fl = B * len(steps) * 301.851e9
-        print(f"B={B} steps={len(steps)}: {ms:.1f} ms, {ms/len(steps):.2f} ms/step, {fl/ms/1e9:.1f} TFLOP/s, "
+        # 2*MAC per patch per call: 301.851 GFLOP at base_ch 96; the 3x3 / transposed convs scale with base_ch^2
+        fl = B * len(steps) * (301.851e9 if BASE_CH == 96 else 134.394e9)
+        print(f"base_ch={BASE_CH} B={B} steps={len(steps)}: {ms:.1f} ms, {ms/len(steps):.2f} ms/step, {fl/ms/1e9:.1f} TFLOP/s, "
               f"{B/(ms/1e3)*len(steps)/50:.2f} DDIM-50-equivalent patches/s", flush=True)
 
 
