@@ -467,6 +467,35 @@ def test_drivers_write_reference_outputs(env, tmp_path):
     rows = list(__import__("csv").reader(open(odir / "d" / "ddim_true_infer_metrics.csv")))
     assert rows[0][-3:] == ["PSNR_mean", "SAM_mean", "ERGAS_mean"] and len(rows) == 6
     drivers.main(["onestep", "--out_dir", str(odir / "e"), "--t_small", "20"] + common)
+    # Evaluation_Pure_Generation.py --mode night_demo: generation without a target, first --save_viz_n files; .npy instead of PNG
+    drivers.main(["night_demo", "--out_dir", str(odir / "n"), "--t_start", "999", "--ddim_steps", "3", "--save_viz_n", "3"] + common)
+    night = sorted(os.listdir(odir / "n" / "viz"))
+    assert night == [f"{i:03d}_night_{k}.npy" for i in range(3) for k in ("cond", "pred")]
+    pred = np.load(odir / "n" / "viz" / "001_night_pred.npy")
+    assert pred.shape == (4, 32, 32) and pred.min() >= 0.0 and pred.max() <= 1.0
+    assert np.array_equal(np.load(odir / "n" / "viz" / "001_night_cond.npy"), np.load(pdir / "patch_000001.npz")["inputs"])
+    # a file without a 'mask' key counts as all-valid; the masks of the other files of its batch stay in force
+    mdir = tmp_path / "mixed"
+    mdir.mkdir()
+    for i in range(2):
+        d = dict(np.load(pdir / f"patch_{i:06d}.npz"))
+        if i == 1:
+            d.pop("mask")
+        np.savez_compressed(mdir / f"patch_{i:06d}.npz", **d)
+    mixed = ["--patch_dir", str(mdir), "--ckpt", str(ckpt), "--batch", "2", "--t_start_grid", "200", "--ddim_steps_grid", "3"]
+    drivers.main(["ddim_sweep", "--out_dir", str(odir / "m2")] + mixed)
+    for i in range(2):                                      # the same two files one at a time: same per-file seeds and noise
+        one = tmp_path / f"one{i}"
+        one.mkdir()
+        os.link(mdir / f"patch_{i:06d}.npz", one / f"patch_{i:06d}.npz")
+    rows2 = list(__import__("csv").reader(open(odir / "m2" / "ddim_sweep_summary.csv")))
+    drivers.main(["ddim_sweep", "--out_dir", str(odir / "m0"), "--patch_dir", str(tmp_path / "one0"), "--ckpt", str(ckpt), "--batch", "1",
+                  "--t_start_grid", "200", "--ddim_steps_grid", "3"])
+    drivers.main(["ddim_sweep", "--out_dir", str(odir / "m1"), "--patch_dir", str(tmp_path / "one1"), "--ckpt", str(ckpt), "--batch", "1",
+                  "--t_start_grid", "200", "--ddim_steps_grid", "3", "--seed_base", "1235"])
+    r0 = list(__import__("csv").reader(open(odir / "m0" / "ddim_sweep_summary.csv")))[1]
+    r1 = list(__import__("csv").reader(open(odir / "m1" / "ddim_sweep_summary.csv")))[1]
+    assert abs(float(rows2[1][3]) - 0.5 * (float(r0[3]) + float(r1[3]))) <= 2e-6       # MAE_mean of the mixed batch
     # per-patch results do not depend on the batch size
     drivers.main(["ddim_sweep", "--out_dir", str(odir / "f"), "--t_start_grid", "200", "--ddim_steps_grid", "3",
                   "--patch_dir", str(pdir), "--ckpt", str(ckpt), "--batch", "1"])
