@@ -182,6 +182,10 @@ int s1s2_profile_layers(s1s2_handle* h, int B, int reps, float* ms_out, int n_ou
  * the activation / weight operand once its shared-memory ring is full, to attribute time to data movement; the
  * arena contents are garbage afterwards when perf_mode != 0. */
 int s1s2_debug_loop_layer(s1s2_handle* h, int B, int layer, int reps, int perf_mode, float* ms_out, void* stream);
+/* Measurement / test aid: the GEMM-N tile width (output channels per tile; 4 x Cout columns for the transposed convs) the
+ * i-th launch of a model call uses at batch B -- narrower tiles are picked when the wide ones cannot fill the GPU (small
+ * batches); every choice computes bit-identical results.  -1 for a bad argument. */
+int s1s2_debug_tile_width(s1s2_handle* h, int layer, int B);
 /* state_dict prefix of the i-th launch of a model call ("inc.0", "down1.0.0", ... "conv1.2"), NULL past the end. */
 const char* s1s2_layer_name(const s1s2_handle* h, int i);
 

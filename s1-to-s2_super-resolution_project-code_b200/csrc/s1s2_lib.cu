@@ -1204,6 +1204,13 @@ int s1s2_debug_activation(s1s2_handle* h, const char* name, float* out_nchw, int
     return S1S2_ERR_INVALID;
 }
 
+int s1s2_debug_tile_width(s1s2_handle* h, int layer, int B) {
+    if (h == nullptr || layer < 0 || layer >= static_cast<int>(h->layers.size()) || B < 1 || B > h->max_batch) return -1;
+    const Layer& L = h->layers[layer];
+    const Layer::Alt* alt = pick_variant(h, L, B);
+    return kernel_table()[alt != nullptr ? alt->kid : L.kid].block_n;
+}
+
 const char* s1s2_layer_name(const s1s2_handle* h, int i) {
     if (h == nullptr || i < 0 || i >= static_cast<int>(h->layers.size())) return nullptr;
     return h->layers[i].name;

@@ -51,6 +51,7 @@ SIGNATURES = {
     "s1s2_debug_saturation_count": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int),
                                               C.c_void_p]),
     "s1s2_view_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "s1s2_debug_tile_width": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "s1s2_layer_name": (C.c_char_p, [C.c_void_p, C.c_int]),
     "s1s2_tile_extract": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

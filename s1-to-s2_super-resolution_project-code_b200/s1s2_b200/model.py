@@ -147,6 +147,18 @@ class UNetSmallB200(nn.Module):
         _lib.check(L.s1s2_profile_layers(eng.h, batch, reps, ms, n.value, C.byref(n), C.c_void_p(stream)), eng.h)
         return [(L.s1s2_layer_name(eng.h, i).decode(), float(ms[i])) for i in range(n.value)]
 
+    def tile_widths(self, device, H: int, W: int, batch: int):
+        """[(state_dict prefix, GEMM-N tile width)] the launches of a model call use at this batch (s1s2_debug_tile_width)."""
+        eng = self.engine(torch.device(device), H, W, batch)
+        L = _lib.lib()
+        out, i = [], 0
+        while True:
+            name = L.s1s2_layer_name(eng.h, i)
+            if name is None:
+                return out
+            out.append((name.decode(), int(L.s1s2_debug_tile_width(eng.h, i, batch))))
+            i += 1
+
     def loop_layer(self, device, H: int, W: int, batch: int, layer: int, reps: int, perf_mode: int = 0) -> float:
         """Mean ms per launch of one layer run alone `reps` times (s1s2_debug_loop_layer; measurement aid)."""
         eng = self.engine(torch.device(device), H, W, batch)

@@ -190,6 +190,23 @@ def test_small_batch_tilings_do_not_change_bits(env):
     del plain
 
 
+def test_tile_width_choice_by_batch(env):
+    """pick_variant: the widest tile at large batches (least weight traffic per flop), narrower ones where the wide tiles
+    would leave most of the 74 CTA pairs idle (the 64 x 64 layers of a single 256 x 256 patch have 16 pairs of M tiles)."""
+    import s1s2_b200
+    dev = env["dev"]
+    m = s1s2_b200.UNetSmallB200(8, 4, 96, max_batch=64).to(dev)
+    m.load_state_dict(env["sd"], strict=True)
+    w64 = dict(m.tile_widths(dev, 256, 256, 64))
+    w1 = dict(m.tile_widths(dev, 256, 256, 1))
+    assert w64["down3.0.2"] == 256 and w64["conv3.0"] == 192 and w64["down2.0.2"] == 192 and w64["conv1.0"] == 96
+    assert w64["up3"] == 256 and w64["up1"] == 192 and w64["inc.0"] == 96 and w64["conv1.2"] == 96
+    assert w1["down3.0.2"] == 192 and w1["down3.0.0"] == 192 and w1["conv3.0"] == 96 and w1["conv3.2"] == 96
+    assert all(w1[k] <= w64[k] for k in w64)
+    assert len(w64) == 16
+    del m
+
+
 def _scaled_sd(sd, g):
     return {k: (v * g if k.endswith(".weight") and not k.startswith("outc") else v.clone()) for k, v in sd.items()}
 
