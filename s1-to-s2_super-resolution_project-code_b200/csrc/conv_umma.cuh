@@ -182,18 +182,20 @@ __device__ __forceinline__ void prefetch_next_weights(const uint8_t* w, uint32_t
 }
 
 template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, int SBUF = 1, int TPS = 1,
-          int HSLOTS = kHaloSlotsDefault>
+          int HSLOTS = kHaloSlotsDefault, int SUBC = 32>
 struct ConvSmem {
     static constexpr int kABox = 128 * KBOX * 2;
     static constexpr int kBBox = (BLOCK_N / CTAS) * KBOX * 2;   // this CTA's share of the weight rows
     static constexpr int kARing = HALO ? HSLOTS * Halo<KBOX>::kSlot : 0;
     static constexpr int kStage = HALO ? TPS * kBBox : BOXES * (kABox + kBBox);   // halo mode: the ring holds weight tiles only
                                                                                   // (TPS taps of one channel chunk per stage)
-    // output staging for the TMA store: one [rows][32 channels] fp16 sub-tile (64-byte rows, 64B swizzle) per
-    // 32-column accumulator chunk; rows = 128 pixels, or the 32 pooled pixels of the tile
+    // output staging for the TMA store: [rows][SUBC channels] fp16 sub-tiles -- SUBC = 32: 64-byte rows, 64B swizzle, one
+    // sub-tile per 32-column accumulator chunk; SUBC = 64: 128-byte rows, 128B swizzle, one per two chunks (half as many
+    // rows for the TMA unit to write; needs Cout % 64 == 0); rows = 128 pixels, or the 32 pooled pixels of the tile
     static constexpr int kSubRows = MODE == MODE_POOL ? 32 : 128;
-    static constexpr int kSubBytes = kSubRows * 64;
-    static constexpr int kStagingBuf = (MODE != MODE_HEAD) ? (BLOCK_N / 32) * kSubBytes : 0;
+    static constexpr int kSubBytes = kSubRows * SUBC * 2;
+    static constexpr int kStagingBuf = (MODE != MODE_HEAD) ? (BLOCK_N / SUBC) * kSubBytes : 0;
+    static_assert(SUBC == 32 || (SUBC == 64 && BLOCK_N % 64 == 0 && MODE != MODE_HEAD), "staging sub-tile width");
     static constexpr int kStaging = SBUF * kStagingBuf;       // SBUF > 1: short-K layers, where a tile is shorter than a
                                                               // TMA store's smem-read latency
     static constexpr int kBias = 1536 * 4;
@@ -242,12 +244,12 @@ __device__ __forceinline__ float range_scale(uint32_t amax_bits, float& s) {
 // named barrier over 384 threads costs more than the 2 + 1 chunk imbalance it removes).
 // HSLOTS: depth of the activation halo ring (3; deeper for inc.0, whose 6 KB halo tiles are pure TMA latency).
 template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, bool WRES = false, int SBUF = 1,
-          int TPS = 1, int EPIWG = 1, int HSLOTS = kHaloSlotsDefault>
+          int TPS = 1, int EPIWG = 1, int HSLOTS = kHaloSlotsDefault, int SUBC = 32>
 __global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(128 + 128 * EPIWG, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
     static_assert(!WRES || (HALO && TPS == 9 && STAGES == 1), "resident weights: halo mode, all nine taps in one stage");
     static_assert(EPIWG == 1 || (EPIWG == 2 && MODE != MODE_HEAD), "epilogue warpgroups");
-    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE, CTAS, HALO, SBUF, TPS, HSLOTS>;
+    using L = ConvSmem<BLOCK_N, KBOX, BOXES, STAGES, MODE, CTAS, HALO, SBUF, TPS, HSLOTS, SUBC>;
     constexpr int kHaloSlots = HSLOTS;            // activation halo ring depth (halo mode)
     constexpr bool kPair = CTAS == 2;
     constexpr bool kTmaStore = (MODE != MODE_HEAD);
@@ -768,12 +770,23 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     }
                     if constexpr (kTmaStore) {
                         if (writer) {
-                            uint8_t* row = sout + c * L::kSubBytes + srow * 64;
-                            const int sw = (srow >> 1) & 3;                            // 64B swizzle: chunk ^= row[2:1]
-                            *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-                            *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
-                            *reinterpret_cast<uint4*>(row + ((2 ^ sw) << 4)) = make_uint4(h[8], h[9], h[10], h[11]);
-                            *reinterpret_cast<uint4*>(row + ((3 ^ sw) << 4)) = make_uint4(h[12], h[13], h[14], h[15]);
+                            if constexpr (SUBC == 32) {
+                                uint8_t* row = sout + c * L::kSubBytes + srow * 64;
+                                const int sw = (srow >> 1) & 3;                        // 64B swizzle: chunk ^= row[2:1]
+                                *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+                                *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+                                *reinterpret_cast<uint4*>(row + ((2 ^ sw) << 4)) = make_uint4(h[8], h[9], h[10], h[11]);
+                                *reinterpret_cast<uint4*>(row + ((3 ^ sw) << 4)) = make_uint4(h[12], h[13], h[14], h[15]);
+                            } else {
+                                // 128-byte rows: this 32-column chunk is the lower / upper half of its 64-channel sub-tile
+                                uint8_t* row = sout + (c >> 1) * L::kSubBytes + srow * 128;
+                                const int sw = srow & 7;                               // 128B swizzle: chunk ^= row[2:0]
+                                const int j0 = (c & 1) << 2;
+                                *reinterpret_cast<uint4*>(row + (((j0 + 0) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+                                *reinterpret_cast<uint4*>(row + (((j0 + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+                                *reinterpret_cast<uint4*>(row + (((j0 + 2) ^ sw) << 4)) = make_uint4(h[8], h[9], h[10], h[11]);
+                                *reinterpret_cast<uint4*>(row + (((j0 + 3) ^ sw) << 4)) = make_uint4(h[12], h[13], h[14], h[15]);
+                            }
                         }
                     }
                 }
@@ -790,8 +803,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                             // tile = a plain box of the 5-D view (c, kx, x, y, n) of the output rows of parity ky
                             const int ix0 = tx << p.tw_log2, iy0 = ty << p.th_log2;
 #pragma unroll
-                            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                                const int ng = n_tile * BLOCK_N + c * 32;
+                            for (int c = 0; c < BLOCK_N / SUBC; ++c) {
+                                const int ng = n_tile * BLOCK_N + c * SUBC;
                                 const int tap = ng / p.cout;
                                 tma_store_5d((tap >> 1) ? &p.tmap_out2 : &p.tmap_out, sout + c * L::kSubBytes, ng - tap * p.cout,
                                              tap & 1, ix0, iy0, on0);
@@ -800,8 +813,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                             const int sh = MODE == MODE_POOL ? 1 : 0;
                             const int ox0 = (tx << p.tw_log2) >> sh, oy0 = (ty << p.th_log2) >> sh;
 #pragma unroll
-                            for (int c = 0; c < BLOCK_N / 32; ++c)
-                                tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, n_tile * BLOCK_N + c * 32, ox0, oy0, on0);
+                            for (int c = 0; c < BLOCK_N / SUBC; ++c)
+                                tma_store_4d(&p.tmap_out, sout + c * L::kSubBytes, n_tile * BLOCK_N + c * SUBC, ox0, oy0, on0);
                         }
                         bulk_commit();
                     }

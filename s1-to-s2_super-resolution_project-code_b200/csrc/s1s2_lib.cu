@@ -205,15 +205,17 @@ enum KernelId { K_INC = 0, K_C96IN, K_STORE, K_POOL, K_CONVT, K_STORE256, K_POOL
 struct KernelInfo {
     void (*fn)(const ConvParams);
     int block_n, kbox, boxes, smem, mode, ctas, threads;
+    int subc;                // channels per output staging sub-tile = inner box of the store tensor map (32 or 64)
     bool px;                 // conv_px_kernel (pixels on N) instead of conv_umma_kernel
     bool halo;               // conv_umma_kernel halo mode (8 x 16 tile, one activation halo tile per chunk)
 };
 
 template <int BN, int KB, int BX, int ST, int MODE, int CTAS = 2, bool HALO = false, bool WRES = false, int SBUF = 1,
-          int TPS = 1, int EPIWG = 1, int HSLOTS = kHaloSlotsDefault>
+          int TPS = 1, int EPIWG = 1, int HSLOTS = kHaloSlotsDefault, int SUBC = 32>
 KernelInfo make_kernel() {
     KernelInfo k;
-    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS, HALO, WRES, SBUF, TPS, EPIWG, HSLOTS>;
+    k.fn = conv_umma_kernel<BN, KB, BX, ST, MODE, CTAS, HALO, WRES, SBUF, TPS, EPIWG, HSLOTS, SUBC>;
+    k.subc = SUBC;
     k.threads = 128 + 128 * EPIWG;
     k.ctas = CTAS;
     k.px = false;
@@ -221,7 +223,7 @@ KernelInfo make_kernel() {
     k.block_n = BN;
     k.kbox = KB;
     k.boxes = BX;
-    k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS, HALO, SBUF, TPS, HSLOTS>::kBytes;
+    k.smem = ConvSmem<BN, KB, BX, ST, MODE, CTAS, HALO, SBUF, TPS, HSLOTS, SUBC>::kBytes;
     k.mode = MODE;
     return k;
 }
@@ -230,6 +232,7 @@ template <int KB, int ST, int MODE, int TPS = 1, int HSLOTS = 2, int NQ = 3>
 KernelInfo make_px_kernel() {
     KernelInfo k;
     k.fn = conv_px_kernel<KB, ST, MODE, TPS, HSLOTS, NQ>;
+    k.subc = 32;
     k.threads = kPxThreads;
     k.block_n = 32 * NQ;
     k.kbox = KB;
@@ -254,16 +257,19 @@ struct KernelTable {
         t[K_CONVT] = make_kernel<192, 64, 1, 6, MODE_CONVT>();
         t[K_STORE256] = make_kernel<256, 64, 1, 4, MODE_STORE>();
         t[K_POOL256] = make_kernel<256, 64, 1, 6, MODE_POOL>();
-        t[K_CONVT256] = make_kernel<256, 64, 1, 4, MODE_CONVT>();
+        t[K_CONVT256] = make_kernel<256, 64, 1, 4, MODE_CONVT, 2, false, false, 1, 1, 1, kHaloSlotsDefault, 64>();   // 128-byte store rows
         t[K_N96] = make_kernel<96, 64, 1, 8, MODE_STORE>();     // Cout = 96
-        t[K_HSTORE] = make_kernel<192, 64, 1, 8, MODE_STORE, 2, true>();    // halo mode (default for 3x3, Cin % 64 == 0)
-        t[K_HPOOL] = make_kernel<192, 64, 1, 10, MODE_POOL, 2, true>();
-        t[K_HSTORE256] = make_kernel<256, 64, 1, 5, MODE_STORE, 2, true>();
-        t[K_HPOOL256] = make_kernel<256, 64, 1, 8, MODE_POOL, 2, true>();
+        // halo mode (default for 3x3, Cin % 64 == 0); 64-channel (128-byte) rows in the output staging: the TMA unit writes a
+        // tile row by row, and with 64-byte rows the stores of a short-K tile (down1.0.0, the transposed convs) took as long
+        // as its MMAs
+        t[K_HSTORE] = make_kernel<192, 64, 1, 8, MODE_STORE, 2, true, false, 1, 1, 1, kHaloSlotsDefault, 64>();
+        t[K_HPOOL] = make_kernel<192, 64, 1, 10, MODE_POOL, 2, true, false, 1, 1, 1, kHaloSlotsDefault, 64>();
+        t[K_HSTORE256] = make_kernel<256, 64, 1, 5, MODE_STORE, 2, true, false, 1, 1, 1, kHaloSlotsDefault, 64>();
+        t[K_HPOOL256] = make_kernel<256, 64, 1, 8, MODE_POOL, 2, true, false, 1, 1, 1, kHaloSlotsDefault, 64>();
         // Short-K layers: several taps per ring stage (the MMA issue loop costs ~300 cycles per stage: ncu source view)
         t[K_HINC] = make_kernel<96, 16, 1, 1, MODE_STORE, 2, true, true, 4, 9, 2, 8>();   // inc.0: 32-byte rows, nine resident weight
                                                                   // tiles, 4 staging buffers, two epilogue warpgroups, 8 halo slots
-        t[K_HC96IN] = make_kernel<192, 32, 1, 6, MODE_STORE, 2, true, false, 1, 3>();  // down1.0.0: exact K = 96 per tap as three
+        t[K_HC96IN] = make_kernel<192, 32, 1, 6, MODE_STORE, 2, true, false, 1, 3, 1, kHaloSlotsDefault, 64>();  // down1.0.0: exact K = 96 per tap as three
                                                                                        // 32-channel chunks, one kernel row per stage
         t[K_PX_STORE] = make_px_kernel<64, 5, MODE_STORE>();            // conv1.0: pixels on N (see conv_px.cuh)
         t[K_PX_HEAD32] = make_px_kernel<32, 4, MODE_HEAD, 3, 3>();        // same with exact 32-channel chunks, one kernel row per
@@ -280,9 +286,9 @@ struct KernelTable {
         // kernels above serve Cout = 256 / 512 and the three transposed convs; these cover Cout = 128 and 64 (three taps
         // per stage for the same reason as the 96-column tiles), the first layer and the head.
         t[K_HINC64] = make_kernel<64, 16, 1, 1, MODE_STORE, 2, true, true, 4, 9, 2, 8>();
-        t[K_HSTORE128] = make_kernel<128, 64, 1, 4, MODE_STORE, 2, true, false, 1, 3>();
-        t[K_HPOOL128] = make_kernel<128, 64, 1, 5, MODE_POOL, 2, true, false, 1, 3>();
-        t[K_HSTORE64] = make_kernel<64, 64, 1, 8, MODE_STORE, 2, true, false, 1, 3>();
+        t[K_HSTORE128] = make_kernel<128, 64, 1, 4, MODE_STORE, 2, true, false, 1, 3, 1, kHaloSlotsDefault, 64>();
+        t[K_HPOOL128] = make_kernel<128, 64, 1, 5, MODE_POOL, 2, true, false, 1, 3, 1, kHaloSlotsDefault, 64>();
+        t[K_HSTORE64] = make_kernel<64, 64, 1, 8, MODE_STORE, 2, true, false, 1, 3, 1, kHaloSlotsDefault, 64>();
         t[K_PX_HEAD64] = make_px_kernel<32, 4, MODE_HEAD, 3, 3, 2>();
     }
 };
@@ -528,11 +534,15 @@ int build_layer_params(s1s2_handle* h, Layer& L, KernelId kid, ConvParams& p, st
         cuuint64_t dims[5] = {static_cast<cuuint64_t>(L.cout), 2, static_cast<cuuint64_t>(Wl), static_cast<cuuint64_t>(Hl),
                               static_cast<cuuint64_t>(h->nalloc)};
         cuuint64_t strides[4] = {pb, 2 * pb, 2 * Wo * pb, static_cast<cuuint64_t>(Ho) * Wo * pb};
-        cuuint32_t box[5] = {32u, 1u, 1u << g.tw_log2, 1u << g.th_log2, static_cast<cuuint32_t>(g.tn)};
+        if (L.cout % k.subc != 0) {
+            set_err(err, "layer %s: %d output channels per tap do not fit %d-channel store sub-tiles", L.name, L.cout, k.subc);
+            return S1S2_ERR_INVALID;
+        }
+        cuuint32_t box[5] = {static_cast<cuuint32_t>(k.subc), 1u, 1u << g.tw_log2, 1u << g.th_log2, static_cast<cuuint32_t>(g.tn)};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         for (int ky = 0; ky < 2; ++ky) {
             CUresult r = enc(ky ? &p.tmap_out2 : &p.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, L.dst + static_cast<size_t>(ky) * Wo * L.dst_pitch,
-                             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(k.subc),
                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {
                 set_err(err, "layer %s: output tensor map (ky %d) rejected (CUresult %d)", L.name, ky, static_cast<int>(r));
@@ -552,10 +562,10 @@ int build_layer_params(s1s2_handle* h, Layer& L, KernelId kid, ConvParams& p, st
                               static_cast<cuuint64_t>(h->nalloc)};
         cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.dst_pitch) * 2, static_cast<cuuint64_t>(Wo) * L.dst_pitch * 2,
                                  static_cast<cuuint64_t>(Ho) * Wo * L.dst_pitch * 2};
-        cuuint32_t box[4] = {32u, (1u << g.tw_log2) >> sh, (1u << g.th_log2) >> sh, static_cast<cuuint32_t>(g.tn)};
+        cuuint32_t box[4] = {static_cast<cuuint32_t>(k.subc), (1u << g.tw_log2) >> sh, (1u << g.th_log2) >> sh, static_cast<cuuint32_t>(g.tn)};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&p.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, L.dst, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(k.subc), CU_TENSOR_MAP_L2_PROMOTION_NONE,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_err(err, "layer %s: output tensor map rejected (CUresult %d)", L.name, static_cast<int>(r));

@@ -76,7 +76,12 @@ def lib():
                             "s1s2_b200 has no CPU or PyTorch fallback")
         L = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(L, name)
+            try:
+                fn = getattr(L, name)
+            except AttributeError:
+                if path == LIB_PATH:
+                    raise
+                continue             # an older build under S1S2_LIB may lack the newest debug entries
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
