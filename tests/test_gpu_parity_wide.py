@@ -419,3 +419,40 @@ def test_base64_batch_independent(env64):
     t = torch.tensor([999, 501, 20], dtype=torch.long).to(dev)
     y = env64["model"](xin, t).clone()
     assert torch.equal(env64["model"](xin[1:2], t[1:2])[0], y[1])
+
+
+# ------------------------------------------------------------------------------------------------ DDPM, full length
+def test_ddpm_1000_full_chain(env):
+    """Limitation_Test.py:209-224 at its real length: the ancestral chain over all T = 1000 timesteps (999 noisy steps), one
+    32 x 32 patch.  (a) supplied z: every one of the 1000 scheduler updates bit-exact, the predicted eps checked against the
+    fp32 oracle on our state at every 20th call; (b) in-kernel Philox noise: finite, clamped, reproducible for a seed."""
+    from s1s2_b200 import samplers, schedule
+    dev = env["dev"]
+    betas = osched.cosine_betas(1000)
+    alphas = 1 - betas
+    ab = torch.cumprod(alphas, 0)
+    assert torch.equal(ab, env["abar"])
+    x, cond = _inputs(1, 32, 32, seed=800)
+    zs = torch.randn((999, 1, 4, 32, 32), generator=torch.Generator().manual_seed(801))
+    steps = schedule.steps_ddpm(betas, alphas, ab, "eps")
+    assert len(steps) == 1000 and steps[0].t == 999 and steps[-1].t == 0
+    out, taps = samplers.run_steps(env["model"], steps, cond.to(dev), x.to(dev), step_noise=zs.to(dev), tap_pred=True, tap_x=True)
+    torch.cuda.synchronize()
+    preds, xs = taps["pred"].cpu(), taps["x"].cpu()
+    x_in, worst = x.clone(), 0.0
+    for i, st in enumerate(steps):
+        if i % 20 == 0 or i == 999:
+            ref = env["oracle"](torch.cat([x_in, cond], 1), torch.full((1,), st.t, dtype=torch.long))
+            rel = float((preds[i] - ref).norm() / ref.norm())
+            assert rel <= 5e-3, (i, st.t, rel)
+            worst = max(worst, rel)
+        z = zs[st.noise_index] if st.noise_index >= 0 else None
+        want = _ref_update(st, x_in, preds[i], z)
+        assert torch.equal(xs[i], want), (i, st.t)
+        x_in = xs[i]
+    assert torch.equal(out.cpu(), x_in) and float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    a = samplers.ddpm_sample(env["model"], cond.to(dev), betas, alphas, ab, 4, noise=x.to(dev), seed=5).clone()
+    b = samplers.ddpm_sample(env["model"], cond.to(dev), betas, alphas, ab, 4, noise=x.to(dev), seed=5)
+    c = samplers.ddpm_sample(env["model"], cond.to(dev), betas, alphas, ab, 4, noise=x.to(dev), seed=6)
+    assert torch.equal(a, b) and not torch.equal(a, c) and bool(torch.isfinite(a).all())
+    print(f"[DDPM-1000] 1000 updates bit-exact, eps checked on 51 calls: worst rel-L2 {worst:.2e}")
