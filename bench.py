@@ -23,6 +23,7 @@ The default line carries, besides the contract keys:
   gpu_library_baseline  the same oracle module on `cuda` = PyTorch eager + cuDNN, the path the unmodified reference takes on
                         this GPU: TF32 batch 1 (the scripts as written) and fp16 autocast + channels_last batch 64 (best case)
   latency   the batch 1..16 table of the `latency` workload (rank 0, N = 1)
+  other_configs  BASELINE configs 1, 2 and 4 in short form (N = 1): one denoiser call at batch 1, eps16, the step-count sweep
   scene     config 5 at this N: one 2048^2 scene at stride 64 and at Patch.py's default stride 32, with per-phase times
             and the sha256 of the stitched canvas (must not depend on N)
 
@@ -377,6 +378,69 @@ def latency_table(model, abar, dev, batches=(1, 2, 4, 8, 16), target_s=0.8):
     return rows
 
 
+def other_configs_block(model_v, abar, dev):
+    """The remaining BASELINE configs in the driver-visible line (N = 1): config 1 as the host-visible latency of one
+    denoiser call at batch 1 (Onestep.py:149-164 runs exactly one), config 2 (eps model, grid A 999 -> 0, batch 16) and
+    config 4 (v model, 10 / 25 / 50 / 100 / 250 steps at batch 64); one timed chain each, device time by CUDA events."""
+    import torch
+    from s1s2_b200 import samplers, schedule
+    out = {}
+    # config 1
+    cond, noise = synthetic_batch(1, 5001)
+    x = torch.cat([noise, cond], 1).to(dev)
+    t = torch.full((1,), 20, dtype=torch.long, device=dev)
+    for _ in range(5):
+        model_v(x, t)
+    torch.cuda.synchronize()
+    lat = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        y = model_v(x, t)
+        torch.cuda.synchronize()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    out["onestep_b1"] = {"what": "one model(torch.cat([x_t, x_cond], 1), t_idx) call at batch 1, host-visible (call + synchronize)",
+                         "ms_median": round(statistics.median(lat), 4), "ms_min": round(min(lat), 4), "finite": bool(torch.isfinite(y).all())}
+    # config 4
+    B = model_v.max_batch
+    cond_h, noise_h = synthetic_batch(B, 2024)
+    cond_d, noise_d = cond_h.to(dev), noise_h.to(dev)
+    init_scale = float(torch.sqrt(1 - abar[999]))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rows = []
+    for n_steps in (10, 25, 50, 100, 250):
+        steps = schedule.steps_grid_b(abar, schedule.grid_b(999, n_steps), "v")
+        e0.record()
+        res = samplers.run_steps(model_v, steps, cond_d, noise_d, init_scale=init_scale)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        rows.append({"ddim_steps": n_steps, "model_calls": len(steps), "ms_per_chain": round(ms, 2),
+                     "ms_per_model_call": round(ms / len(steps), 4), "patches_per_s": round(B / (ms / 1e3), 2)})
+        assert bool(torch.isfinite(res).all())
+    out["sweep_v64"] = {"what": "DDIM_Sweep (config 4): v model, grid B from 999, batch %d, one chain per step count" % B, "rows": rows}
+    del cond_d, noise_d
+    # config 2
+    model_e = build_model(SEED_EPS, 16, dev)
+    steps = schedule.steps_eps_grid_a(abar, 999, 50)
+    cond_h, noise_h = synthetic_batch(16, 2025)
+    cond_d, noise_d = cond_h.to(dev), noise_h.to(dev)
+    samplers.run_steps(model_e, steps, cond_d, noise_d)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        res = samplers.run_steps(model_e, steps, cond_d, noise_d)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    out["eps16"] = {"what": "DDIM_Multi-step / Evaluation_Pure_Generation (config 2): eps model, grid A 999 -> 0 (50 calls), batch 16",
+                    "ms_per_chain": round(ms, 2), "patches_per_s": round(16 / (ms / 1e3), 2),
+                    "frac_of_peak": round(FLOP_PER_CALL * N_CALLS * 16 / (ms / 1e3) / 1e12 / peaks()[0], 4),
+                    "finite": bool(torch.isfinite(res).all())}
+    del model_e
+    torch.cuda.empty_cache()
+    return out
+
+
 def scene_block(model, abar, dev, rank, world, batch):
     """BASELINE config 5 at this world size: one synthetic 4 x 2048 x 2048 Sentinel-1 scene held in pinned HOST memory, uploaded,
     tiled by Patch.py's rule (256 / stride 64 = 841 windows, and Patch.py's default stride 32 = 3249), patch-sharded over the
@@ -588,10 +652,11 @@ def main():
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-scene", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--quick", action="store_true", help="main arm only (no cpu / library baselines, latency table, scene block)")
     args = ap.parse_args()
     if args.quick:
-        args.no_cpu_baseline = args.no_latency = args.no_library_baseline = args.no_scene = True
+        args.no_cpu_baseline = args.no_latency = args.no_library_baseline = args.no_scene = args.no_configs = True
     if args.batch is None:
         args.batch = 16 if args.workload == "eps16" else 64
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -727,8 +792,10 @@ def main():
         top = max(roof["layers"], key=lambda r: r["ms"])
         roof["dominant_launch"] = top
 
-    lat = lib = None
+    lat = lib = other = None
     if rank == 0 and world == 1:
+        if not args.no_configs and args.workload == "v64":
+            other = other_configs_block(model, abar, dev)
         if not args.no_latency:
             lat = latency_table(model, abar, dev)
         if not args.no_library_baseline:
@@ -751,7 +818,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic", "config": config_block(args, world), "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "gpu_library_baseline": lib, "latency": lat, "scene": scene}
+                "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "gpu_library_baseline": lib, "latency": lat, "scene": scene,
+                "other_configs": other}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
