@@ -343,7 +343,8 @@ def cmd_scene(args):
     t0 = time.perf_counter()
     res = sc.generate_scene(model, scene, alpha_bar, ps=args.patch_size, stride=args.stride, param=args.param,
                             steps=args.ddim_steps, t_start=args.t_start, batch=args.batch, seed_base=args.seed_base,
-                            valid_ratio_threshold=args.valid_ratio_threshold, rank=rank, world=world)
+                            valid_ratio_threshold=args.valid_ratio_threshold, rank=rank, world=world,
+                            window=None if args.blend == "uniform" else args.blend)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -394,6 +395,7 @@ def main(argv=None):
     ap.add_argument("--patch_size", type=int, default=256)
     ap.add_argument("--stride", type=int, default=64)
     ap.add_argument("--valid_ratio_threshold", type=float, default=0.0)
+    ap.add_argument("--blend", default="uniform", choices=["uniform", "hann"], help="overlap blend of the scene stitch")
     args = ap.parse_args(argv)
     if args.cmd == "onestep":
         cmd_onestep(args)
