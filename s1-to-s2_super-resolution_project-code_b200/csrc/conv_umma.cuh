@@ -31,6 +31,8 @@
 // layer adds bias/s, the head multiplies its output by s.  ReLU, max-pool and the convolutions are positively
 // homogeneous, so this is the same network; with k = 0 it is bit-identical to the unscaled arithmetic.
 #pragma once
+#include <type_traits>
+
 #include "ptx_sm100.cuh"
 
 namespace s1s2 {
@@ -76,6 +78,27 @@ struct HeadParams {
     StepCoef step;                // by value: kind == STEP_NONE for a plain forward
 };
 
+// Division by a launch-constant divisor without the ~40-instruction integer-division sequence: the tile -> (n_tile, tx, ty,
+// image) decomposition runs once per tile in every role, and for the short-K layers (first layer, transposed convs) the
+// epilogue's instruction count per tile is what bounds the kernel (ncu source view: ~190 of ~520 epilogue instructions
+// per tile of inc.0 were these divisions).  mul == 0: power of two (shift only); else q = umulhi(n, mul) >> shr, exact for
+// n < 2^31 (mul = ceil(2^(31 + ceil_log2 d) / d), the classic round-up multiplier).
+struct FastDiv {
+    uint32_t mul, shr, d;
+    __host__ static FastDiv make(uint32_t d) {
+        FastDiv f;
+        f.d = d;
+        uint32_t lg = 0;
+        while ((1u << lg) < d) ++lg;                       // ceil_log2
+        if ((1u << lg) == d) { f.mul = 0; f.shr = lg; return f; }
+        const unsigned p = 31 + lg;
+        f.mul = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
+        f.shr = p - 32;
+        return f;
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return mul != 0 ? (__umulhi(n, mul) >> shr) : (n >> shr); }
+};
+
 struct ConvParams {
     CUtensorMap tmap_a;
     CUtensorMap tmap_b;
@@ -92,6 +115,7 @@ struct ConvParams {
     int tw_log2, th_log2;         // M tile = TN x TH x TW = 128 pixels
     int tiles_x, tiles_y;
     int num_m_tiles, num_n_tiles;
+    FastDiv fd_n, fd_tx, fd_ty;   // divisions by num_n_tiles, tiles_x, tiles_y (conv_umma_kernel's tile decomposition)
     int taps_w;                   // 3 -> 3x3 pad 1 ; 1 -> 1x1 / transposed-conv GEMM
     int chunks;                   // K chunks of KBOX channels per tap
     int tap_kstride;              // conv_px_kernel: K columns between consecutive taps in the weight rows (= Cin)
@@ -124,6 +148,22 @@ struct ConvParams {
 #define S1S2_TL_ONCE(flag, slot) do { } while (0)
 #define S1S2_TL_GRID(slot, op) do { } while (0)
 #endif
+
+// group tile index -> N tile and the M tile's position (tile column / row inside an image, image index) of CTA `rank`
+struct TileCoord { int n_tile, tx, ty, tn; };
+template <int CTAS>
+__device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile, uint32_t rank) {
+    TileCoord c;
+    const uint32_t mq = p.fd_n.div(static_cast<uint32_t>(tile));
+    c.n_tile = tile - static_cast<int>(mq) * p.num_n_tiles;
+    const uint32_t m_tile = CTAS * mq + rank;
+    const uint32_t row = p.fd_tx.div(m_tile);
+    c.tx = static_cast<int>(m_tile - row * static_cast<uint32_t>(p.tiles_x));
+    const uint32_t img = p.fd_ty.div(row);
+    c.ty = static_cast<int>(row - img * static_cast<uint32_t>(p.tiles_y));
+    c.tn = static_cast<int>(img);
+    return c;
+}
 
 // Halo mode (3x3 layers with Cin % 64 == 0): the M tile is 8 wide x 16 tall and its activations are fetched ONCE per
 // 64-channel chunk as an 18 x 10 pixel halo tile; the nine taps read it through UMMA descriptors whose start address
@@ -343,10 +383,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         int s = 0, sa = 0;
         uint32_t ph = 0, pha = 0;
         auto load_halo = [&](int tile, int chunk) {
-            const int m_tile = CTAS * (tile / p.num_n_tiles) + static_cast<int>(rank);
-            const int tx = m_tile % p.tiles_x;
-            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-            const int tn = m_tile / (p.tiles_x * p.tiles_y);       // past the batch for a phantom tile: zero fill
+            const TileCoord tc = tile_coord<CTAS>(p, tile, rank);
+            const int tx = tc.tx, ty = tc.ty, tn = tc.tn;          // tn past the batch for a phantom tile: zero fill
             mbar_wait(&aempty_bar[sa], pha ^ 1);
             const uint32_t bar = kPair ? mapa_shared(smem_u32(&afull_bar[sa]), 0) : smem_u32(&afull_bar[sa]);
             if (elect_one()) {
@@ -386,7 +424,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             if (++s == STAGES) { s = 0; ph ^= 1; }
         };
         [[maybe_unused]] int tap0 = 0;
-        [[maybe_unused]] const int b_row_first = (tile % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
+        [[maybe_unused]] const int b_row_first = tile_coord<CTAS>(p, tile, rank).n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
         if constexpr (!WRES) {
             if (tile < num_tiles)
                 for (; tap0 < 9 && tap0 < STAGES * TPS; tap0 += TPS) weight_stage(b_row_first, tap0 * p.tap_kstride, false);
@@ -411,7 +449,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         }
         while (tile < num_tiles) {
             if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
-            const int b_row0 = (tile % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
+            const int b_row0 = tile_coord<CTAS>(p, tile, rank).n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
             int kcol = chunk * KBOX;
             for (int tap = 0; tap < (WRES ? 0 : 9); tap += TPS, kcol += TPS * p.tap_kstride) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
@@ -522,11 +560,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         S1S2_TL(2);
         S1S2_TL(3);
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-            const int n_tile = tile % p.num_n_tiles;
-            const int m_tile = CTAS * (tile / p.num_n_tiles) + static_cast<int>(rank);
-            const int tx = m_tile % p.tiles_x;
-            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-            const int tn = m_tile / (p.tiles_x * p.tiles_y);
+            const TileCoord tc = tile_coord<CTAS>(p, tile, rank);
+            const int n_tile = tc.n_tile, tx = tc.tx, ty = tc.ty, tn = tc.tn;
             const int x0 = (tx << p.tw_log2) - pad;
             const int y0 = (ty << p.th_log2) - pad;
             const int n0 = tn << (7 - p.tw_log2 - p.th_log2);    // past the batch for a phantom tile: zero fill
@@ -622,11 +657,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             uint8_t* sout = sout0 + sbuf * L::kStagingBuf;
             if (++sbuf == SBUF) sbuf = 0;
-            const int n_tile = tile % p.num_n_tiles;
-            const int m_tile = CTAS * (tile / p.num_n_tiles) + static_cast<int>(rank);
-            const int tx = m_tile % p.tiles_x;
-            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-            const int tn = m_tile / (p.tiles_x * p.tiles_y);
+            const TileCoord tc = tile_coord<CTAS>(p, tile, rank);
+            const int n_tile = tc.n_tile, tx = tc.tx, ty = tc.ty, tn = tc.tn;
             const int x = (tx << p.tw_log2) + lx;
             const int y = (ty << p.th_log2) + ly;
             const int n = (tn << (7 - p.tw_log2 - p.th_log2)) + ln;
@@ -745,49 +777,54 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 const bool first = (p.flags & LAYER_FLAG_FIRST) != 0;
                 const float s_bias = first ? 1.f : s_dn;      // first layer: unscaled inputs, scale the result
                 const float s_post = first ? s_dn : 1.f;
-#pragma unroll
-                for (int cc = 0; cc < kChunksWg; ++cc) {
-                    const int c = c_lo + cc;
-                    if (EPIWG > 1 && c >= kChunks) break;
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c * 32, r);
+                // One segment of WD accumulator columns starting at col0: TMEM -> bias / ReLU / scale -> fp16 (-> 2x2 max) -> staging.
+                auto segment = [&](auto wd_tag, const int col0) {
+                    constexpr int WD = decltype(wd_tag)::value;
+                    uint32_t r[WD];
+                    if constexpr (WD == 32) tmem_ld32(taddr + col0, r); else tmem_ld16(taddr + col0, r);
                     tmem_ld_wait();
-                    uint32_t h[16];
+                    uint32_t h[WD / 2];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float a = fmaf(bias_t[c * 32 + 2 * j], s_bias, __uint_as_float(r[2 * j]));
-                        float b = fmaf(bias_t[c * 32 + 2 * j + 1], s_bias, __uint_as_float(r[2 * j + 1]));
+                    for (int j = 0; j < WD / 2; ++j) {
+                        float a = fmaf(bias_t[col0 + 2 * j], s_bias, __uint_as_float(r[2 * j]));
+                        float b = fmaf(bias_t[col0 + 2 * j + 1], s_bias, __uint_as_float(r[2 * j + 1]));
                         if constexpr (MODE != MODE_CONVT) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                         if constexpr (MODE == MODE_STORE) { a *= s_post; b *= s_post; }
                         h[j] = pack_half2_sat(a, b);
                     }
                     if constexpr (MODE == MODE_POOL) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < WD / 2; ++j) {
                             h[j] = hmax2_u32(h[j], __shfl_xor_sync(0xffffffffu, h[j], 1));
                             h[j] = hmax2_u32(h[j], __shfl_xor_sync(0xffffffffu, h[j], tw));
                         }
                     }
                     if constexpr (kTmaStore) {
                         if (writer) {
-                            if constexpr (SUBC == 32) {
-                                uint8_t* row = sout + c * L::kSubBytes + srow * 64;
-                                const int sw = (srow >> 1) & 3;                        // 64B swizzle: chunk ^= row[2:1]
-                                *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-                                *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
-                                *reinterpret_cast<uint4*>(row + ((2 ^ sw) << 4)) = make_uint4(h[8], h[9], h[10], h[11]);
-                                *reinterpret_cast<uint4*>(row + ((3 ^ sw) << 4)) = make_uint4(h[12], h[13], h[14], h[15]);
-                            } else {
-                                // 128-byte rows: this 32-column chunk is the lower / upper half of its 64-channel sub-tile
-                                uint8_t* row = sout + (c >> 1) * L::kSubBytes + srow * 128;
-                                const int sw = srow & 7;                               // 128B swizzle: chunk ^= row[2:0]
-                                const int j0 = (c & 1) << 2;
-                                *reinterpret_cast<uint4*>(row + (((j0 + 0) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-                                *reinterpret_cast<uint4*>(row + (((j0 + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
-                                *reinterpret_cast<uint4*>(row + (((j0 + 2) ^ sw) << 4)) = make_uint4(h[8], h[9], h[10], h[11]);
-                                *reinterpret_cast<uint4*>(row + (((j0 + 3) ^ sw) << 4)) = make_uint4(h[12], h[13], h[14], h[15]);
-                            }
+                            // staging row of this pixel inside the SUBC-channel sub-tile the segment belongs to; 16-byte
+                            // chunk j0 + i of the row, XOR-swizzled like the store tensor map (64B: row[2:1], 128B: row[2:0])
+                            uint8_t* row = sout + (col0 / SUBC) * L::kSubBytes + srow * (SUBC * 2);
+                            const int sw = SUBC == 32 ? ((srow >> 1) & 3) : (srow & 7);
+                            const int j0 = (col0 % SUBC) >> 3;
+#pragma unroll
+                            for (int i = 0; i < WD / 8; ++i)
+                                *reinterpret_cast<uint4*>(row + (((j0 + i) ^ sw) << 4)) =
+                                    make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
                         }
+                    }
+                };
+                using W32 = std::integral_constant<int, 32>;
+                using W16 = std::integral_constant<int, 16>;
+                if constexpr (BLOCK_N == 96 && EPIWG == 2) {
+                    // 96 columns over two warpgroups: 48 each (32 + 16 / 16 + 32) instead of two chunks against one
+                    if (c_lo == 0) { segment(W32{}, 0); segment(W16{}, 32); }
+                    else { segment(W16{}, 48); segment(W32{}, 64); }
+                } else {
+#pragma unroll
+                    for (int cc = 0; cc < kChunksWg; ++cc) {
+                        const int c = c_lo + cc;
+                        if (EPIWG > 1 && c >= kChunks) break;
+                        segment(W32{}, c * 32);
                     }
                 }
                 tc_fence_before();

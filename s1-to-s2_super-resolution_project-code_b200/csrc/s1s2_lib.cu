@@ -254,10 +254,12 @@ struct KernelTable {
         t[K_C96IN] = make_kernel<192, 32, 3, 4, MODE_STORE>();  // Cin = 96 (64-byte swizzle rows)
         t[K_STORE] = make_kernel<192, 64, 1, 6, MODE_STORE>();
         t[K_POOL] = make_kernel<192, 64, 1, 7, MODE_POOL>();
-        t[K_CONVT] = make_kernel<192, 64, 1, 6, MODE_CONVT>();
+        // transposed convs: short K (3 / 6 / 12 stages per tile) under an epilogue of 6 / 8 column chunks -- two epilogue
+        // warpgroups, each draining half of the chunks (ncu source view: one group needed longer than the tile's MMAs)
+        t[K_CONVT] = make_kernel<192, 64, 1, 6, MODE_CONVT, 2, false, false, 1, 1, 2>();
         t[K_STORE256] = make_kernel<256, 64, 1, 4, MODE_STORE>();
         t[K_POOL256] = make_kernel<256, 64, 1, 6, MODE_POOL>();
-        t[K_CONVT256] = make_kernel<256, 64, 1, 4, MODE_CONVT, 2, false, false, 1, 1, 1, kHaloSlotsDefault, 64>();   // 128-byte store rows
+        t[K_CONVT256] = make_kernel<256, 64, 1, 4, MODE_CONVT, 2, false, false, 1, 1, 2, kHaloSlotsDefault, 64>();   // 128-byte store rows
         t[K_N96] = make_kernel<96, 64, 1, 8, MODE_STORE>();     // Cout = 96
         // halo mode (default for 3x3, Cin % 64 == 0); 64-channel (128-byte) rows in the output staging: the TMA unit writes a
         // tile row by row, and with 64-byte rows the stores of a short-K tile (down1.0.0, the transposed convs) took as long
@@ -584,6 +586,9 @@ int build_layer_params(s1s2_handle* h, Layer& L, KernelId kid, ConvParams& p, st
     p.tiles_y = g.tiles_y;
     p.num_m_tiles = 0;
     p.num_n_tiles = L.ntot / k.block_n;
+    p.fd_n = FastDiv::make(static_cast<uint32_t>(p.num_n_tiles));
+    p.fd_tx = FastDiv::make(static_cast<uint32_t>(p.tiles_x));
+    p.fd_ty = FastDiv::make(static_cast<uint32_t>(p.tiles_y));
     p.taps_w = L.taps_w;
     p.chunks = L.cin / k.kbox;
     p.tap_kstride = L.cin;

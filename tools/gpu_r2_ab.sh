@@ -1,9 +1,9 @@
 #!/bin/bash
-# same-box A/B of two builds of the library (batch 64 quick line + batch 1..16 latency): ab_libs/lib_r2h.so vs the in-tree one
+# same-box A/B of two builds of the library (batch 64 quick line + batch 1..16 latency): ab_libs/lib_r2n.so vs the in-tree one
 set -u
 O=gpurun_out
 if [ "${1:-}" = "tests" ]; then timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3; fi
-for V in "" "S1S2_LIB=$PWD/ab_libs/lib_r2h.so" "" "S1S2_LIB=$PWD/ab_libs/lib_r2h.so"; do
+for V in "" "S1S2_LIB=$PWD/ab_libs/lib_r2n.so" "" "S1S2_LIB=$PWD/ab_libs/lib_r2n.so"; do
   env $V python bench.py --quick --steps 4 > $O/ab.json 2>> $O/ab.err
   env $V python bench.py --workload latency --no-library-baseline --no-layers > $O/ab_lat.json 2>> $O/ab.err
   python - "$V" <<PY
