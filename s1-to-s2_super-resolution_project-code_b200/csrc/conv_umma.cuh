@@ -440,15 +440,22 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         for (int d = 0; d < kAhead; ++d)
             if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
         S1S2_TL(3);
+        // Order inside a position.  64-channel chunks: next halo tile first, then this chunk's weights (a chunk is 9 x 4 MMAs,
+        // the halo request is far ahead either way).  32-channel chunks (down1.0.0): WEIGHTS FIRST -- a chunk is only 1728 MMA
+        // cycles, the weight ring holds two chunks, and a halo request that has to wait for its slot (freed two chunks back)
+        // would hold this chunk's weights back with it: ncu's source view showed the MMA warp spending 42 % of its time
+        // waiting for the first weight stage of each chunk, and none on the second and third.
+        constexpr bool kWeightsFirst = KBOX == 32;
         if constexpr (!WRES) {                    // the first position, peeled: its first weight stages are already in flight
             if (tile < num_tiles) {
-                if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
+                if (!kWeightsFirst && htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
                 for (; tap0 < 9; tap0 += TPS) weight_stage(b_row_first, tap0 * p.tap_kstride, true);
+                if (kWeightsFirst && htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
                 advance(tile, chunk);
             }
         }
         while (tile < num_tiles) {
-            if (htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
+            if (!kWeightsFirst && htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
             const int b_row0 = tile_coord<CTAS>(p, tile, rank).n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / CTAS);
             int kcol = chunk * KBOX;
             for (int tap = 0; tap < (WRES ? 0 : 9); tap += TPS, kcol += TPS * p.tap_kstride) {
@@ -464,6 +471,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 __syncwarp();
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
+            if (kWeightsFirst && htile < num_tiles) { load_halo(htile, hchunk); advance(htile, hchunk); }
             advance(tile, chunk);
         }
     } else if (HALO && warp == 1) {
