@@ -79,13 +79,18 @@ def peaks():
 
 
 def csrc_fingerprint():
-    """sha256 (16 hex) over the kernel sources: an ncu capture is only quoted while the kernels it profiled are unchanged."""
+    """sha256 (16 hex) over the kernel sources with comments and whitespace removed: an ncu capture is only quoted while
+    the code it profiled is unchanged (editing a comment does not invalidate it; editing a kernel does)."""
+    import re
     h = hashlib.sha256()
     d = os.path.join(PKG, "csrc")
     for name in sorted(os.listdir(d)):
         if name.endswith((".cu", ".cuh")):
+            text = open(os.path.join(d, name), encoding="utf-8").read()
+            text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)          # block comments
+            text = re.sub(r"//[^\n]*", "", text)                       # line comments (no string literal here holds "//")
             h.update(name.encode())
-            h.update(open(os.path.join(d, name), "rb").read())
+            h.update(re.sub(r"\s+", "", text).encode())
     return h.hexdigest()[:16]
 
 

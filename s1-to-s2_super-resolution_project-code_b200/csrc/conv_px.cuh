@@ -1,8 +1,10 @@
-// Pixels-on-N convolution kernel for the narrow (Cout = 96) full-resolution layers: conv1.0 and conv1.2 (+ outc + scheduler).
+// Pixels-on-N convolution kernel for the head layer: conv1.2 (+ outc + scheduler), Cout = 96 (or 64).
 //
-// The measured cost of one tcgen05.mma is ~128 cycles per 128 M rows for ANY N <= 256 (profiles/r1_attribution_loops.txt),
-// so conv_umma_kernel, which puts Cout on N, runs a Cout = 96 layer at 96/256 = 37.5 % of the tensor pipe.  Here the
-// GEMM is transposed:
+// (Round 1 built it for both Cout = 96 layers on the reading that one tcgen05.mma costs ~128 cycles for any N; that
+// experiment was issue-bound -- an MMA takes N/2 cycles -- and conv1.0 now runs 8 % faster on conv_umma_kernel with
+// 96-column tiles and three taps per stage.  For the head the pixels-on-N form still wins: its two epilogue warpgroups
+// work on different tiles, while the Cout-on-N head has one group doing the 96 x 4 head FMAs of every pixel)
+// Here the GEMM is transposed:
 //
 //   D^T[cout, pixel] = sum_{tap, cin} Wt[cout, tap, cin] * X[pixel shifted by tap, cin]
 //

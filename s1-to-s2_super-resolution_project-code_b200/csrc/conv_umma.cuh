@@ -275,13 +275,13 @@ __device__ __forceinline__ float range_scale(uint32_t amax_bits, float& s) {
 // (M = 128), kept for A/B measurements of the pairing itself.
 // TPS (halo mode): weight tiles of TPS consecutive taps (one kernel row, or all nine) of a channel chunk share one ring
 // stage and one barrier round trip, and the MMA warp issues them from a fully unrolled block with compile-time
-// descriptor offsets.  The issue loop costs ~300 cycles per stage whatever it carries (ncu source view, r1s profiles), so
-// short-K stages (KBOX = 16 / 32: one / two 128-cycle MMAs per tap) were issue-bound at TPS = 1.
+// descriptor offsets.  The issue loop costs ~300 cycles per stage whatever it carries (ncu source view, r1s profiles), and an
+// MMA N/2 cycles, so stages of few or narrow MMAs (KBOX = 16 / 32: one / two MMAs per tap; N <= 128) are issue-bound at TPS = 1.
 // WRES (halo mode, one chunk per tap, TPS = 9, one stage): the nine weight tiles are loaded once per CTA and stay
 // resident; the ring then only carries activation halo tiles (inc.0).
-// EPIWG: epilogue warpgroups (warps 4..7 [, 8..11]); with two, each drains half of the accumulator's 32-column chunks
-// (inc.0: its tiles are only nine MMAs long, so the epilogue is the long pole; a third group measured 3 % slower -- the
-// named barrier over 384 threads costs more than the 2 + 1 chunk imbalance it removes).
+// EPIWG: epilogue warpgroups (warps 4..7 [, 8..11]); with two, each drains half of the accumulator's columns (the first
+// layer and the transposed convs: their tiles are 9 / 12 ... 48 MMAs long, so the epilogue's instruction count per tile is
+// the long pole; 96 columns are split 48 / 48; a third group measured neutral).
 // HSLOTS: depth of the activation halo ring (3; deeper for inc.0, whose 6 KB halo tiles are pure TMA latency).
 template <int BLOCK_N, int KBOX, int BOXES, int STAGES, int MODE, int CTAS, bool HALO = false, bool WRES = false, int SBUF = 1,
           int TPS = 1, int EPIWG = 1, int HSLOTS = kHaloSlotsDefault, int SUBC = 32>

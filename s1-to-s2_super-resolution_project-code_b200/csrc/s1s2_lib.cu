@@ -248,8 +248,10 @@ KernelInfo make_px_kernel() {
 struct KernelTable {
     KernelInfo t[K_COUNT];
     KernelTable() {
-        // UMMA time per instruction is ~128 cycles (one M row per cycle) whatever N <= 256 is, so N = 256 tiles are
-        // used wherever the GEMM N (Cout, or 4*Cout for the transposed convs) is a multiple of 256.
+        // One tcgen05.mma (128 rows per CTA, K = 16) occupies the tensor pipe for N/2 cycles; the widest tile that divides
+        // the GEMM N (Cout, or 4*Cout for the transposed convs) costs the least weight traffic and issue work per flop:
+        // N = 256 where N % 256 == 0, else 192 / 128 / 96 / 64.  The first block are the round-1 one-box-per-tap kernels,
+        // kept as A/B baselines (S1S2_NO_HALO) and for the transposed convs.
         t[K_INC] = make_kernel<96, 16, 3, 4, MODE_STORE>();     // Cin = 16-channel pixel record
         t[K_C96IN] = make_kernel<192, 32, 3, 4, MODE_STORE>();  // Cin = 96 (64-byte swizzle rows)
         t[K_STORE] = make_kernel<192, 64, 1, 6, MODE_STORE>();
