@@ -28,3 +28,31 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_traffic_stamp_belongs_to_these_kernels():
+    """profiles/traffic.json (the ncu --set full DRAM bytes bench.py quotes as roofline.traffic) was captured on exactly the
+    kernel sources in the tree; bench.py drops the number the moment csrc/ changes (comments and whitespace aside)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    assert tj["csrc_fingerprint"] == bench.csrc_fingerprint()
+    assert 15.0 < tj["dram_total_GB"] < 20.0 and len(tj["layers"]) == 16
+
+
+def test_fingerprint_ignores_comments(tmp_path, monkeypatch):
+    sys.path.insert(0, ROOT)
+    import bench
+    src = os.path.join(bench.PKG, "csrc")
+    dst = tmp_path / "pkg" / "csrc"
+    dst.mkdir(parents=True)
+    for name in os.listdir(src):
+        text = open(os.path.join(src, name)).read()
+        (dst / name).write_text(text)
+    monkeypatch.setattr(bench, "PKG", str(tmp_path / "pkg"))
+    base = bench.csrc_fingerprint()
+    f = dst / "conv_px.cuh"
+    f.write_text("// a new comment\n" + f.read_text() + "\n/* another\n one */\n")
+    assert bench.csrc_fingerprint() == base
+    f.write_text(f.read_text().replace("kPxThreads = 384", "kPxThreads = 256"))
+    assert bench.csrc_fingerprint() != base
